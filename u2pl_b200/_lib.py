@@ -1,0 +1,66 @@
+"""ctypes binding of libu2pl_b200.so (the C ABI declared in include/u2pl_b200.h).
+
+There is no fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libu2pl_b200.so")
+
+_P = c_void_p       # device pointer
+_S = c_void_p       # cudaStream_t
+
+# name -> (restype, argtypes).  tests/test_cabi_symbols.py checks this table against the header.
+SIGNATURES = {
+    "u2pl_abi_version": (c_int, []),
+    "u2pl_last_error": (c_char_p, []),
+    "u2pl_launch_count": (c_int64, []),
+    "u2pl_entropy_ws_bytes": (c_size_t, [c_int64, c_int64]),
+    "u2pl_entropy_thresholds": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, POINTER(c_float), c_int,
+                                        _P, _P, _P, _P, c_size_t, _S]),
+    "u2pl_partition_target": (c_int, [_P, _P, c_int64, c_int64, _P, c_int, _P, _P, _S]),
+    "u2pl_entropy_masks": (c_int, [_P, _P, _P, c_int64, c_int64, _P, c_int, c_int, _P, _P, _S]),
+    "u2pl_ce_ws_bytes": (c_size_t, [c_int64, c_int64]),
+    "u2pl_ce_forward": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_size_t, _S]),
+    "u2pl_ce_backward": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _S]),
+    "u2pl_unsup_finalize": (c_int, [_P, _P, c_int64, _P, _P, _P, _S]),
+}
+
+_lib = None
+
+
+class U2PLNativeError(RuntimeError):
+    pass
+
+
+def load(build_if_missing=True):
+    """Load (building first if needed) libu2pl_b200.so and attach prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise U2PLNativeError(f"{LIB_PATH} is missing; run `python -m u2pl_b200.build`")
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library drift: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.u2pl_abi_version() != 1:
+        raise U2PLNativeError("libu2pl_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().u2pl_last_error()
+        raise U2PLNativeError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count():
+    return int(load().u2pl_launch_count())

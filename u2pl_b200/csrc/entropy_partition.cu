@@ -1,0 +1,456 @@
+// entropy_partition.cu -- fused softmax-entropy + on-device percentile thresholds +
+// reliable/unreliable partition.  Replaces loss_helper.py:35-44 and
+// train_semi.py:402-418 of the reference (ATen softmax/log/sum, boolean gather,
+// D2H copy, np.percentile on the host, mask algebra) with
+//
+//   K1  entropy_hist    one pass over the [B,C,HW] logits: entropy out, order-preserving
+//                       uint32 keys out, 12-bit radix histogram of the valid keys
+//   K2  select1         ranks lo/hi of every requested percentile (numpy float32 index
+//                       arithmetic) + the 12-bit bin each rank falls in
+//   K3  hist_refine(2)  10-bit histogram inside those bins      (keys are L2 resident)
+//   K4  select_refine   K5 hist_refine(3)   K6 select_refine -> thresholds (two-sided lerp)
+//   K7  partition       target rewrite + drop mask + kept count
+//
+// HBM-bound by design: K1 moves (4C + 8 + 4 + 4) B/pixel, K7 moves 4+8+8+1 B/pixel,
+// K3/K5 re-read 4 B/pixel of keys out of the 126 MB L2.  Nothing synchronises the host.
+#include "arith.cuh"
+#include "common.cuh"
+
+namespace u2pl {
+
+constexpr int kMaxQ = U2PL_MAX_QUANTILES;
+constexpr int kMaxT = 2 * kMaxQ;          // (lo, hi) order statistic per percentile
+constexpr int kBins1 = 4096;              // pass 1: key bits 31..20
+constexpr int kBinsR = 1024;              // pass 2: bits 19..10, pass 3: bits 9..0
+constexpr uint32_t kInvalidKey = 0xFFFFFFFFu;
+
+struct SelState {
+    uint32_t prefix[kMaxT];
+    uint32_t rank[kMaxT];
+    float    gamma[kMaxQ];
+    uint32_t n;
+    uint32_t pad[3];
+};
+
+struct Percents { float q[kMaxQ]; };
+
+// ------------------------------------------------------------------ K1
+template <int C>
+__device__ __forceinline__ float entropy_of(float (&v)[C])
+{
+    float m = v[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmaxf(m, v[c]);
+    float S = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        v[c] = det_expf(__fadd_rn(v[c], -m));
+        S = __fadd_rn(S, v[c]);
+    }
+    const float rinv = __fdiv_rn(1.0f, S);
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float p = __fmul_rn(v[c], rinv);
+        const float l = det_logf(__fadd_rn(p, 1e-10f));
+        acc = __fmaf_rn(p, l, acc);
+    }
+    return -acc;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+entropy_hist_kernel(const float *__restrict__ logits, const int64_t *__restrict__ target,
+                    uint32_t HW, uint32_t N, int64_t ignore,
+                    float *__restrict__ ent, uint32_t *__restrict__ keys,
+                    uint32_t *__restrict__ hist1)
+{
+    __shared__ uint32_t sh[kBins1];
+    for (int j = threadIdx.x; j < kBins1; j += 256) sh[j] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < N; i += gridDim.x * 256u) {
+        const uint32_t b = i / HW, p = i - b * HW;
+        const float *x = logits + static_cast<size_t>(b) * C * HW + p;
+        float v[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
+        const int64_t t = __ldg(target + i);
+        const float h = entropy_of<C>(v);
+        ent[i] = h;
+        const bool valid = (t != ignore);
+        const uint32_t key = valid ? float_key(h) : kInvalidKey;
+        keys[i] = key;
+        if (valid) atomicAdd(&sh[key >> 20], 1u);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < kBins1; j += 256)
+        if (sh[j]) atomicAdd(&hist1[j], sh[j]);
+}
+
+// Any class count: three passes over the C axis per pixel (max, sum, entropy); same
+// arithmetic, same operation order, identical bits -- only slower (L1/L2 re-reads).
+__global__ void __launch_bounds__(256)
+entropy_hist_kernel_anyC(const float *__restrict__ logits, const int64_t *__restrict__ target,
+                         uint32_t C, uint32_t HW, uint32_t N, int64_t ignore,
+                         float *__restrict__ ent, uint32_t *__restrict__ keys,
+                         uint32_t *__restrict__ hist1)
+{
+    __shared__ uint32_t sh[kBins1];
+    for (int j = threadIdx.x; j < kBins1; j += 256) sh[j] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < N; i += gridDim.x * 256u) {
+        const uint32_t b = i / HW, p = i - b * HW;
+        const float *x = logits + static_cast<size_t>(b) * C * HW + p;
+        float m = __ldg(x);
+        for (uint32_t c = 1; c < C; ++c) m = fmaxf(m, __ldg(x + static_cast<size_t>(c) * HW));
+        float S = 0.0f;
+        for (uint32_t c = 0; c < C; ++c)
+            S = __fadd_rn(S, det_expf(__fadd_rn(__ldg(x + static_cast<size_t>(c) * HW), -m)));
+        const float rinv = __fdiv_rn(1.0f, S);
+        float acc = 0.0f;
+        for (uint32_t c = 0; c < C; ++c) {
+            const float e = det_expf(__fadd_rn(__ldg(x + static_cast<size_t>(c) * HW), -m));
+            const float pr = __fmul_rn(e, rinv);
+            acc = __fmaf_rn(pr, det_logf(__fadd_rn(pr, 1e-10f)), acc);
+        }
+        const float h = -acc;
+        ent[i] = h;
+        const bool valid = (__ldg(target + i) != ignore);
+        const uint32_t key = valid ? float_key(h) : kInvalidKey;
+        keys[i] = key;
+        if (valid) atomicAdd(&sh[key >> 20], 1u);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < kBins1; j += 256)
+        if (sh[j]) atomicAdd(&hist1[j], sh[j]);
+}
+
+// ------------------------------------------------------------------ K2
+// One block of 256 threads, thread t owns bins [16t, 16t+16).
+__global__ void __launch_bounds__(256)
+select1_kernel(const uint32_t *__restrict__ hist1, SelState *__restrict__ st, Percents pc, int nq)
+{
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t s_rank[kMaxT];
+    __shared__ uint32_t s_n;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t loc[16];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { loc[j] = hist1[tid * 16 + j]; sum += loc[j]; }
+    uint32_t inc = sum;                                    // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < wid; ++w) base += warp_tot[w];
+    const uint32_t excl = base + inc - sum;
+    if (tid == 255) s_n = excl + sum;
+    __syncthreads();
+    const uint32_t n = s_n;
+    if (tid == 0) {
+        st->n = n;
+        // numpy 2.x: q32 = q / float32(100); v = float32(n-1) * q32  (all binary32)
+        const float nm1 = __uint2float_rn(n ? n - 1u : 0u);
+        for (int j = 0; j < nq; ++j) {
+            const float q32 = __fdiv_rn(pc.q[j], 100.0f);
+            const float v = __fmul_rn(nm1, q32);
+            const float fl = floorf(v);
+            uint32_t lo, hi;
+            if (n == 0) { lo = hi = 0; }
+            else if (v >= nm1) { lo = hi = n - 1u; }
+            else { lo = static_cast<uint32_t>(fl); hi = lo + 1u; }
+            st->gamma[j] = __fadd_rn(v, -fl);
+            s_rank[2 * j] = lo;
+            s_rank[2 * j + 1] = hi;
+        }
+    }
+    __syncthreads();
+    if (n == 0) return;
+    for (int t = 0; t < 2 * nq; ++t) {
+        const uint32_t r = s_rank[t];
+        if (r >= excl && r < excl + sum) {
+            uint32_t cum = excl;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (r < cum + loc[j]) { st->prefix[t] = tid * 16 + j; st->rank[t] = r - cum; break; }
+                cum += loc[j];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K3 / K5
+// pass 2: match key>>20 against the 12-bit prefix, bin on bits 19..10
+// pass 3: match key>>10 against the 22-bit prefix, bin on bits  9..0
+template <int PASS>
+__global__ void __launch_bounds__(256)
+hist_refine_kernel(const uint32_t *__restrict__ keys, uint32_t N,
+                   const SelState *__restrict__ st, uint32_t *__restrict__ hist, int T)
+{
+    constexpr int kMatchShift = (PASS == 2) ? 20 : 10;
+    constexpr int kBinShift = (PASS == 2) ? 10 : 0;
+    extern __shared__ uint32_t sh[];                      // [T][1024]
+    for (int j = threadIdx.x; j < T * kBinsR; j += 256) sh[j] = 0;
+    uint32_t pre[kMaxT];
+#pragma unroll
+    for (int t = 0; t < kMaxT; ++t) pre[t] = (t < T) ? st->prefix[t] : kInvalidKey;
+    const bool empty = (st->n == 0);
+    __syncthreads();
+    if (!empty) {
+        const uint32_t n4 = N >> 2;
+        const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
+        for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n4; i += gridDim.x * 256u) {
+            const uint4 q = __ldg(k4 + i);
+            const uint32_t kk[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t key = kk[e];
+                if (key == kInvalidKey) continue;
+                const uint32_t hi = key >> kMatchShift;
+                const uint32_t bin = (key >> kBinShift) & (kBinsR - 1);
+#pragma unroll
+                for (int t = 0; t < kMaxT; ++t)
+                    if (t < T && hi == pre[t]) atomicAdd(&sh[t * kBinsR + bin], 1u);
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (N & 3u)) {
+            const uint32_t key = keys[(n4 << 2) + threadIdx.x];
+            if (key != kInvalidKey) {
+                const uint32_t hi = key >> kMatchShift;
+                const uint32_t bin = (key >> kBinShift) & (kBinsR - 1);
+                for (int t = 0; t < T; ++t)
+                    if (hi == pre[t]) atomicAdd(&sh[t * kBinsR + bin], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < T * kBinsR; j += 256)
+        if (sh[j]) atomicAdd(&hist[j], sh[j]);
+}
+
+// ------------------------------------------------------------------ K4 / K6
+// One block of 1024 threads; thread j owns bin j of the current target's histogram.
+template <bool FINAL>
+__global__ void __launch_bounds__(1024)
+select_refine_kernel(const uint32_t *__restrict__ hist, SelState *__restrict__ st, int nq,
+                     float *__restrict__ thresh, int64_t *__restrict__ n_valid)
+{
+    __shared__ uint32_t warp_tot[32];
+    __shared__ float s_val[kMaxT];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t n = st->n;
+    if (n == 0) {
+        if (FINAL && tid == 0) {
+            for (int j = 0; j < nq; ++j) thresh[j] = __uint_as_float(0x7fc00000u);
+            *n_valid = 0;
+        }
+        return;
+    }
+    for (int t = 0; t < 2 * nq; ++t) {
+        const uint32_t cnt = hist[t * kBinsR + tid];
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < wid; ++w) base += warp_tot[w];
+        const uint32_t excl = base + inc - cnt;
+        const uint32_t r = st->rank[t];
+        const uint32_t pre = st->prefix[t];
+        __syncthreads();                                  // everyone has read rank/prefix/warp_tot
+        if (r >= excl && r < excl + cnt) {
+            const uint32_t np = (pre << 10) | static_cast<uint32_t>(tid);
+            st->prefix[t] = np;
+            st->rank[t] = r - excl;
+            if (FINAL) s_val[t] = key_float(np);
+        }
+        __syncthreads();
+    }
+    if (FINAL && tid == 0) {
+        for (int j = 0; j < nq; ++j) {
+            // numpy _lerp: a + (b-a)*g, and b - (b-a)*(1-g) where g >= 0.5  (mul and add rounded separately)
+            const float a = s_val[2 * j], b = s_val[2 * j + 1], g = st->gamma[j];
+            const float d = __fadd_rn(b, -a);
+            float r = __fadd_rn(a, __fmul_rn(d, g));
+            if (g >= 0.5f) r = __fadd_rn(b, -__fmul_rn(d, __fadd_rn(1.0f, -g)));
+            thresh[j] = r;
+        }
+        *n_valid = static_cast<int64_t>(n);
+    }
+}
+
+// ------------------------------------------------------------------ K7
+__global__ void __launch_bounds__(256)
+partition_kernel(const float *__restrict__ ent, int64_t *__restrict__ target, uint32_t N,
+                 int64_t ignore, const float *__restrict__ thresh, int idx,
+                 uint8_t *__restrict__ drop_mask, unsigned long long *__restrict__ n_kept)
+{
+    const float th = __ldg(thresh + idx);
+    int kept = 0;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < N; i += gridDim.x * 256u) {
+        const int64_t t = target[i];
+        const bool valid = (t != ignore);
+        const bool drop = valid && (ent[i] >= th);
+        if (drop) target[i] = ignore;
+        if (drop_mask) drop_mask[i] = drop ? 1 : 0;
+        kept += (valid && !drop) ? 1 : 0;
+    }
+    kept = warp_sum_i(kept);
+    __shared__ int wsum[8];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = kept;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < 8; ++w) s += wsum[w];
+        if (s) atomicAdd(n_kept, static_cast<unsigned long long>(s));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+entropy_masks_kernel(const float *__restrict__ ent, const int64_t *__restrict__ target,
+                     const int64_t *__restrict__ idx, uint32_t n_out, int64_t ignore,
+                     const float *__restrict__ thresh, int lo_idx, int hi_idx,
+                     float *__restrict__ out_low, float *__restrict__ out_high)
+{
+    const float tl = __ldg(thresh + lo_idx), thh = __ldg(thresh + hi_idx);
+    for (uint32_t j = blockIdx.x * 256u + threadIdx.x; j < n_out; j += gridDim.x * 256u) {
+        const int64_t s = idx ? __ldg(idx + j) : static_cast<int64_t>(j);
+        const float e = __ldg(ent + s);
+        const bool valid = (__ldg(target + s) != ignore);
+        if (out_low) out_low[j] = (valid && e <= tl) ? 1.0f : 0.0f;
+        if (out_high) out_high[j] = (valid && e >= thh) ? 1.0f : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+struct EntropyWs {
+    uint32_t *keys, *hist1, *hist2, *hist3;
+    SelState *st;
+    size_t zero_bytes;          // hist1..st are contiguous, zeroed per call
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+static size_t ws_layout(int64_t N, void *base, EntropyWs *out)
+{
+    size_t off = 0;
+    const size_t keys_b = align256(static_cast<size_t>(N) * 4 + 16);
+    const size_t h1 = align256(kBins1 * 4), hr = align256(kMaxT * kBinsR * 4), stb = align256(sizeof(SelState));
+    if (out) {
+        char *p = static_cast<char *>(base);
+        out->keys = reinterpret_cast<uint32_t *>(p + off);
+        out->hist1 = reinterpret_cast<uint32_t *>(p + keys_b);
+        out->hist2 = reinterpret_cast<uint32_t *>(p + keys_b + h1);
+        out->hist3 = reinterpret_cast<uint32_t *>(p + keys_b + h1 + hr);
+        out->st = reinterpret_cast<SelState *>(p + keys_b + h1 + 2 * hr);
+        out->zero_bytes = h1 + 2 * hr + stb;
+    }
+    off = keys_b + h1 + 2 * hr + stb;
+    return off;
+}
+
+static int grid_for(const void *kernel, int threads, size_t smem, uint32_t N, int per_thread = 1)
+{
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long need = (static_cast<long long>(N) + threads * per_thread - 1) / (threads * per_thread);
+    const long long cap = static_cast<long long>(sms) * per_sm;       // one resident wave, grid-stride
+    return static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+template <int C>
+static void launch_entropy(const float *logits, const int64_t *target, uint32_t HW, uint32_t N,
+                           int64_t ignore, float *ent, const EntropyWs &w, cudaStream_t s)
+{
+    const int grid = grid_for(reinterpret_cast<const void *>(entropy_hist_kernel<C>), 256, 0, N);
+    entropy_hist_kernel<C><<<grid, 256, 0, s>>>(logits, target, HW, N, ignore, ent, w.keys, w.hist1);
+}
+
+}  // namespace u2pl
+
+using namespace u2pl;
+
+extern "C" size_t u2pl_entropy_ws_bytes(int64_t B, int64_t HW)
+{
+    return ws_layout(B * HW, nullptr, nullptr);
+}
+
+extern "C" int u2pl_entropy_thresholds(const float *logits, const int64_t *target,
+                                       int64_t B, int64_t C, int64_t HW, int64_t ignore,
+                                       const float *h_percents, int nq,
+                                       float *entropy, float *thresh, int64_t *n_valid,
+                                       void *ws, size_t ws_bytes, void *stream)
+{
+    if (B <= 0 || C <= 0 || HW <= 0) return bad_arg("entropy_thresholds: empty shape");
+    if (nq < 1 || nq > kMaxQ) return bad_arg("entropy_thresholds: nq must be in [1, U2PL_MAX_QUANTILES]");
+    if (B * HW >= (1LL << 31) || B * C * HW >= (1LL << 40)) return bad_arg("entropy_thresholds: B*HW must be < 2^31");
+    if (ws_bytes < ws_layout(B * HW, nullptr, nullptr)) { set_error("entropy_thresholds: workspace too small"); return U2PL_E_WS_SMALL; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t N = static_cast<uint32_t>(B * HW), hw = static_cast<uint32_t>(HW);
+    EntropyWs w;
+    ws_layout(B * HW, ws, &w);
+    cudaError_t e = cudaMemsetAsync(w.hist1, 0, w.zero_bytes, s);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
+    Percents pc;
+    for (int j = 0; j < kMaxQ; ++j) pc.q[j] = (j < nq) ? h_percents[j] : 0.0f;
+
+    switch (C) {
+        case 19: launch_entropy<19>(logits, target, hw, N, ignore, entropy, w, s); break;
+        case 21: launch_entropy<21>(logits, target, hw, N, ignore, entropy, w, s); break;
+        default: {
+            const int grid = grid_for(reinterpret_cast<const void *>(entropy_hist_kernel_anyC), 256, 0, N);
+            entropy_hist_kernel_anyC<<<grid, 256, 0, s>>>(logits, target, static_cast<uint32_t>(C), hw, N,
+                                                          ignore, entropy, w.keys, w.hist1);
+        }
+    }
+    int rc = check_launch("entropy_hist");
+    if (rc) return rc;
+    select1_kernel<<<1, 256, 0, s>>>(w.hist1, w.st, pc, nq);
+    const int T = 2 * nq;
+    const size_t smem = static_cast<size_t>(T) * kBinsR * 4;
+    const int g2 = grid_for(reinterpret_cast<const void *>(hist_refine_kernel<2>), 256, smem, N, 4);
+    hist_refine_kernel<2><<<g2, 256, smem, s>>>(w.keys, N, w.st, w.hist2, T);
+    select_refine_kernel<false><<<1, 1024, 0, s>>>(w.hist2, w.st, nq, thresh, n_valid);
+    hist_refine_kernel<3><<<g2, 256, smem, s>>>(w.keys, N, w.st, w.hist3, T);
+    select_refine_kernel<true><<<1, 1024, 0, s>>>(w.hist3, w.st, nq, thresh, n_valid);
+    return check_launch("entropy_thresholds select chain", 5);
+}
+
+extern "C" int u2pl_partition_target(const float *entropy, int64_t *target, int64_t n, int64_t ignore,
+                                     const float *thresh, int thresh_idx,
+                                     uint8_t *drop_mask, int64_t *n_kept, void *stream)
+{
+    if (n <= 0 || n >= (1LL << 31)) return bad_arg("partition_target: n must be in (0, 2^31)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(n_kept, 0, sizeof(int64_t), s);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
+    const int grid = grid_for(reinterpret_cast<const void *>(partition_kernel), 256, 0, static_cast<uint32_t>(n), 2);
+    partition_kernel<<<grid, 256, 0, s>>>(entropy, target, static_cast<uint32_t>(n), ignore, thresh, thresh_idx,
+                                          drop_mask, reinterpret_cast<unsigned long long *>(n_kept));
+    return check_launch("partition");
+}
+
+extern "C" int u2pl_entropy_masks(const float *entropy, const int64_t *target, const int64_t *idx,
+                                  int64_t n_out, int64_t ignore, const float *thresh, int lo_idx, int hi_idx,
+                                  float *out_low, float *out_high, void *stream)
+{
+    if (n_out <= 0 || n_out >= (1LL << 31)) return bad_arg("entropy_masks: n_out must be in (0, 2^31)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = grid_for(reinterpret_cast<const void *>(entropy_masks_kernel), 256, 0, static_cast<uint32_t>(n_out));
+    entropy_masks_kernel<<<grid, 256, 0, s>>>(entropy, target, idx, static_cast<uint32_t>(n_out), ignore, thresh,
+                                              lo_idx, hi_idx, out_low, out_high);
+    return check_launch("entropy_masks");
+}

@@ -1,0 +1,180 @@
+"""Torch-facing wrappers over the C ABI (include/u2pl_b200.h).
+
+PyTorch is plumbing here: it owns device memory, the current stream and autograd
+bookkeeping; every computation below is a kernel of libu2pl_b200.so.  All functions
+require CUDA tensors and raise otherwise -- there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_WS = {}
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.U2PLNativeError("u2pl_b200 kernels need CUDA tensors (no CPU fallback exists)")
+
+
+def _workspace(name, nbytes, device):
+    key = (name, device)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------- entropy / percentiles
+def entropy_thresholds(logits, target, percents, ignore=255):
+    """Softmax entropy of `logits` [B,C,H,W] + np.percentile-compatible thresholds.
+
+    Mirrors loss_helper.py:35-40 / train_semi.py:402-415.  Returns (entropy [B,H,W] fp32,
+    thresh [len(percents)] fp32 device tensor, n_valid int64 device scalar)."""
+    _need_cuda(logits, target)
+    lib = _lib.load()
+    logits = _f32c(logits)
+    target = target.contiguous()
+    assert target.dtype == torch.int64
+    B, C, H, W = logits.shape
+    HW = H * W
+    nq = len(percents)
+    ent = torch.empty((B, H, W), dtype=torch.float32, device=logits.device)
+    thresh = torch.empty(nq, dtype=torch.float32, device=logits.device)
+    n_valid = torch.empty((), dtype=torch.int64, device=logits.device)
+    nbytes = lib.u2pl_entropy_ws_bytes(B, HW)
+    ws = _workspace("entropy", nbytes, logits.device)
+    hq = (ctypes.c_float * nq)(*[float(q) for q in percents])
+    rc = lib.u2pl_entropy_thresholds(_p(logits), _p(target), B, C, HW, int(ignore), hq, nq,
+                                     _p(ent), _p(thresh), _p(n_valid), _p(ws), ws.numel(), _stream())
+    _lib.check(rc, "u2pl_entropy_thresholds")
+    return ent, thresh, n_valid
+
+
+def partition_target_(entropy, target, thresh, thresh_idx=0, ignore=255, want_mask=False):
+    """In place: target[(entropy >= thresh[idx]) & (target != ignore)] = ignore  (loss_helper.py:41-43).
+    Returns (n_kept int64 device scalar, drop mask uint8 or None)."""
+    _need_cuda(entropy, target, thresh)
+    lib = _lib.load()
+    assert target.is_contiguous() and target.dtype == torch.int64 and entropy.is_contiguous()
+    n = target.numel()
+    mask = torch.empty(target.shape, dtype=torch.uint8, device=target.device) if want_mask else None
+    n_kept = torch.empty((), dtype=torch.int64, device=target.device)
+    rc = lib.u2pl_partition_target(_p(entropy), _p(target), n, int(ignore), _p(thresh), int(thresh_idx),
+                                   _p(mask), _p(n_kept), _stream())
+    _lib.check(rc, "u2pl_partition_target")
+    return n_kept, mask
+
+
+def entropy_masks(entropy, target, thresh, lo_idx, hi_idx, idx=None, ignore=255, out_shape=None):
+    """low/high entropy masks of train_semi.py:408-418, optionally gathered at flat positions `idx`."""
+    _need_cuda(entropy, target, thresh, idx)
+    lib = _lib.load()
+    n_out = idx.numel() if idx is not None else entropy.numel()
+    shape = out_shape if out_shape is not None else (tuple(idx.shape) if idx is not None else tuple(entropy.shape))
+    low = torch.empty(shape, dtype=torch.float32, device=entropy.device)
+    high = torch.empty(shape, dtype=torch.float32, device=entropy.device)
+    rc = lib.u2pl_entropy_masks(_p(entropy), _p(target), _p(idx), n_out, int(ignore), _p(thresh),
+                                int(lo_idx), int(hi_idx), _p(low), _p(high), _stream())
+    _lib.check(rc, "u2pl_entropy_masks")
+    return low, high
+
+
+# --------------------------------------------------------------------------- cross entropy
+def _ce_forward(logits, target, ignore):
+    lib = _lib.load()
+    B, C, H, W = logits.shape
+    nll = torch.empty((), dtype=torch.float32, device=logits.device)
+    n_used = torch.empty((), dtype=torch.int64, device=logits.device)
+    ws = _workspace("ce", lib.u2pl_ce_ws_bytes(B, H * W), logits.device)
+    rc = lib.u2pl_ce_forward(_p(logits), _p(target), B, C, H * W, int(ignore), _p(nll), _p(n_used),
+                             _p(ws), ws.numel(), _stream())
+    _lib.check(rc, "u2pl_ce_forward")
+    return nll, n_used
+
+
+def _ce_backward(logits, target, ignore, scale):
+    lib = _lib.load()
+    B, C, H, W = logits.shape
+    grad = torch.empty_like(logits)
+    rc = lib.u2pl_ce_backward(_p(logits), _p(target), B, C, H * W, int(ignore), _p(scale), _p(grad), _stream())
+    _lib.check(rc, "u2pl_ce_backward")
+    return grad
+
+
+class _CrossEntropyMean(torch.autograd.Function):
+    """nn.CrossEntropyLoss(ignore_index) with mean reduction (loss_helper.py:265,319)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore):
+        _need_cuda(logits, target)
+        logits = _f32c(logits)
+        target = target.contiguous()
+        nll, n_used = _ce_forward(logits, target, ignore)
+        ctx.save_for_backward(logits, target, n_used)
+        ctx.ignore = ignore
+        return nll / n_used.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits, target, n_used = ctx.saved_tensors
+        scale = (gout.to(torch.float32) / n_used.to(torch.float32)).reshape(1).contiguous()
+        return _ce_backward(logits, target, ctx.ignore, scale), None, None
+
+
+def cross_entropy_mean(logits, target, ignore=255):
+    return _CrossEntropyMean.apply(logits, target, ignore)
+
+
+class _UnsupLoss(torch.autograd.Function):
+    """compute_unsupervised_loss (loss_helper.py:30-48) as one fused chain:
+    entropy + percentile + partition (no_grad part) and masked CE (autograd part)."""
+
+    @staticmethod
+    def forward(ctx, predict, target, percent, pred_teacher, ignore):
+        _need_cuda(predict, target, pred_teacher)
+        lib = _lib.load()
+        predict = _f32c(predict)
+        assert target.is_contiguous() and target.dtype == torch.int64
+        ent, thresh, _ = entropy_thresholds(pred_teacher, target, [percent], ignore)
+        n_kept, _ = partition_target_(ent, target, thresh, 0, ignore)         # mutates caller's tensor, like the reference
+        nll, _ = _ce_forward(predict, target, ignore)
+        loss = torch.empty((), dtype=torch.float32, device=predict.device)
+        total = target.numel()
+        rc = lib.u2pl_unsup_finalize(_p(nll), _p(n_kept), total, None, _p(loss), None, _stream())
+        _lib.check(rc, "u2pl_unsup_finalize")
+        ctx.save_for_backward(predict, target, n_kept, nll)
+        ctx.ignore = ignore
+        ctx.total = total
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        predict, target, n_kept, nll = ctx.saved_tensors
+        gout = gout.to(torch.float32).contiguous()
+        scale = torch.empty(1, dtype=torch.float32, device=predict.device)
+        rc = lib.u2pl_unsup_finalize(_p(nll), _p(n_kept), ctx.total, _p(gout), None, _p(scale), _stream())
+        _lib.check(rc, "u2pl_unsup_finalize(bwd)")
+        return _ce_backward(predict, target, ctx.ignore, scale), None, None, None, None
+
+
+def unsup_loss(predict, target, percent, pred_teacher, ignore=255):
+    return _UnsupLoss.apply(predict, target, float(percent), pred_teacher.detach(), ignore)
