@@ -1,0 +1,163 @@
+"""GPU parity: fused entropy / percentile / partition / masked-CE kernels (through the C ABI)
+against the oracle.  Entropies, thresholds and index sets must be BIT-EXACT (arithmetic
+contract); the CE loss and gradient are floating point: |diff| <= 1e-5 relative (north star: 1e-4).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from u2pl_b200 import ops
+    return ops
+
+
+def _dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def _rand_case(rng, B, C, H, W, frac_ignore=0.0, scale=3.0):
+    h, w = max(2, H // 4), max(2, W // 4)
+    x = torch.from_numpy(rng.standard_normal((B, C, h, w)).astype(np.float32)) * scale
+    x = torch.nn.functional.interpolate(x, (H, W), mode="bilinear", align_corners=True).numpy()
+    target = x.argmax(1).astype(np.int64)
+    if frac_ignore > 0:
+        target[rng.random(target.shape) < frac_ignore] = 255
+    return np.ascontiguousarray(x), target
+
+
+@pytest.mark.parametrize("name", ["unsup_c21", "unsup_c19_ignore", "unsup_c5_p100"])
+def test_unsup_loss_golden(golden, name):
+    ops = _ops()
+    g = golden(name)
+    predict = _dev(g["predict"]).requires_grad_(True)
+    target = _dev(g["target_in"], torch.int64)
+    loss = ops.unsup_loss(predict, target, float(g["percent"]), _dev(g["pred_teacher"]))
+    loss.backward()
+    # oracle on the same inputs
+    t_or = g["target_in"].astype(np.int64)
+    out = port.compute_unsupervised_loss(g["predict"], t_or, float(g["percent"]), g["pred_teacher"])
+    assert np.array_equal(target.cpu().numpy(), t_or)                       # bit-exact index set
+    assert abs(loss.item() - float(out["loss"])) <= 1e-5 * abs(float(out["loss"]))
+    assert np.abs(predict.grad.cpu().numpy() - port.unsup_grad(g["predict"], t_or)).max() <= 1e-6
+    # and the reference's own loss value on the same inputs (fixture made by running the reference)
+    if np.array_equal(t_or, g["target_out"].astype(np.int64)):
+        assert abs(loss.item() - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+
+
+@pytest.mark.parametrize("B,C,H,W,ign,percents", [
+    (2, 21, 33, 37, 0.0, [90.0]),
+    (3, 19, 29, 31, 0.3, [80.0, 12.5, 87.5]),
+    (1, 7, 40, 41, 0.1, [100.0, 0.0, 50.0, 99.99]),       # any-C path
+    (2, 2, 17, 19, 0.0, [33.3]),
+    (1, 21, 5, 3, 0.0, [20.0, 80.0]),                     # tiny, ragged
+    (2, 21, 64, 64, 0.95, [95.0]),                        # almost everything ignored
+])
+def test_entropy_thresholds_bit_exact(B, C, H, W, ign, percents):
+    ops = _ops()
+    rng = np.random.default_rng(B * 1000 + C * 10 + H)
+    x, target = _rand_case(rng, B, C, H, W, ign)
+    ent, thresh, n_valid = ops.entropy_thresholds(_dev(x), _dev(target), percents)
+    ent_or = port.entropy(x)
+    assert np.array_equal(ent.cpu().numpy().view(np.uint32), ent_or.view(np.uint32))
+    valid = target != 255
+    assert n_valid.item() == int(valid.sum())
+    th = thresh.cpu().numpy()
+    for j, q in enumerate(percents):
+        want = port.percentile(ent_or[valid], q)
+        assert th[j].view(np.uint32) == np.float32(want).view(np.uint32), (q, th[j], want)
+        assert th[j] == np.percentile(ent_or[valid], q)                     # numpy itself agrees
+
+
+def test_all_ignored_gives_nan():
+    ops = _ops()
+    rng = np.random.default_rng(0)
+    x, target = _rand_case(rng, 1, 21, 16, 16)
+    target[:] = 255
+    ent, thresh, n_valid = ops.entropy_thresholds(_dev(x), _dev(target), [80.0])
+    assert n_valid.item() == 0 and np.isnan(thresh.cpu().numpy()[0])
+    assert np.array_equal(ent.cpu().numpy(), port.entropy(x))
+
+
+def test_heavy_ties_and_constant_logits():
+    ops = _ops()
+    x = np.zeros((2, 21, 24, 24), np.float32)                       # every pixel has the same entropy
+    x[1, 3] = 5.0
+    target = np.zeros((2, 24, 24), np.int64)
+    ent, thresh, _ = ops.entropy_thresholds(_dev(x), _dev(target), [50.0, 99.0])
+    ent_or = port.entropy(x)
+    assert np.array_equal(ent.cpu().numpy(), ent_or)
+    assert thresh.cpu().numpy()[0] == port.percentile(ent_or, 50.0)
+    assert thresh.cpu().numpy()[1] == port.percentile(ent_or, 99.0)
+    t = _dev(target)
+    n_kept, mask = ops.partition_target_(ent, t, thresh, 0, want_mask=True)
+    drop = ent_or >= port.percentile(ent_or, 50.0)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), drop)
+    assert n_kept.item() == int((~drop).sum())
+
+
+def test_entropy_masks_and_gather():
+    ops = _ops()
+    rng = np.random.default_rng(7)
+    x, target = _rand_case(rng, 2, 19, 41, 41, 0.2)
+    ent, thresh, _ = ops.entropy_thresholds(_dev(x), _dev(target), [18.7, 81.3])
+    sy, sx = port.nearest_src_index(11, 41), port.nearest_src_index(11, 41)
+    flat = (np.arange(2)[:, None, None] * 41 * 41 + sy[None, :, None] * 41 + sx[None, None, :]).astype(np.int64)
+    low, high = ops.entropy_masks(ent, _dev(target), thresh, 0, 1, idx=_dev(flat))
+    ent_or = port.entropy(x)
+    valid = target != 255
+    lo_t, hi_t = port.percentile(ent_or[valid], 18.7), port.percentile(ent_or[valid], 81.3)
+    want_low = ((ent_or <= lo_t) & valid).reshape(-1)[flat]
+    want_high = ((ent_or >= hi_t) & valid).reshape(-1)[flat]
+    assert np.array_equal(low.cpu().numpy() > 0, want_low)
+    assert np.array_equal(high.cpu().numpy() > 0, want_high)
+
+
+@pytest.mark.parametrize("C", [21, 19, 6])
+def test_cross_entropy_mean_vs_torch(C):
+    ops = _ops()
+    rng = np.random.default_rng(C)
+    x, target = _rand_case(rng, 2, C, 37, 29, 0.25, scale=2.0)
+    a = _dev(x).requires_grad_(True)
+    b = _dev(x).requires_grad_(True)
+    mine = ops.cross_entropy_mean(a, _dev(target))
+    ref = torch.nn.functional.cross_entropy(b, _dev(target), ignore_index=255)      # torch fp32 reference
+    (mine * 1.7).backward()
+    (ref * 1.7).backward()
+    assert abs(mine.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert (a.grad - b.grad).abs().max().item() <= 1e-7
+    assert abs(mine.item() - float(port.criterion_ce(x, target))) <= 1e-5 * abs(ref.item())
+
+
+def test_full_size_v16_properties():
+    """BASELINE config 2 size (16 x 21 x 513 x 513): size-independent checks.
+    (1) np.percentile of the GPU entropies == the on-device threshold, bitwise;
+    (2) kept count == #(entropy < thresh); (3) a 50k-pixel sample of entropies is bit-equal to the oracle."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    B, C, H, W = 16, 21, 513, 513
+    low = torch.randn(B, C, 129, 129, device="cuda", generator=g) * 3
+    low = torch.nn.functional.avg_pool2d(low, 5, 1, 2, count_include_pad=False)
+    x = torch.nn.functional.interpolate(low, (H, W), mode="bilinear", align_corners=True).contiguous()
+    target = x.argmax(1)
+    percents = [90.0, 10.0, 90.0000001, 100.0]
+    ent, thresh, n_valid = ops.entropy_thresholds(x, target, percents)
+    e = ent.cpu().numpy().ravel()
+    th = thresh.cpu().numpy()
+    for j, q in enumerate(percents):
+        assert th[j] == np.percentile(e, q), q
+    t2 = target.clone()
+    n_kept, _ = ops.partition_target_(ent, t2, thresh, 0)
+    assert n_kept.item() == int((e < th[0]).sum()) == int((t2 != 255).sum().item())
+    assert abs(n_kept.item() / e.size - 0.9) < 1e-3
+    idx = np.random.default_rng(0).choice(B * H * W, 50000, replace=False)
+    xs = x.permute(0, 2, 3, 1).reshape(-1, C)[torch.from_numpy(idx).cuda()].cpu().numpy()      # [50000, C]
+    ent_s = port.entropy(np.ascontiguousarray(xs.T[None]))[0]                                  # B=1, HW=50000
+    assert np.array_equal(ent_s.view(np.uint32), e[idx].view(np.uint32))
