@@ -105,6 +105,86 @@ int u2pl_ce_backward(const float *logits, const int64_t *target, int64_t B, int6
 int u2pl_unsup_finalize(const float *nll_sum, const int64_t *n_kept, int64_t total_pixels,
                         const float *upstream, float *loss, float *bwd_scale, void *stream);
 
+/* ------------------------------------------------------------------------
+ * A9/A10  class-wise memory-bank contrastive loss
+ * replaces: u2pl/utils/loss_helper.py:51-235 (compute_contra_memobank_loss) and
+ *           u2pl/utils/utils.py:28-47 (dequeue_and_enqueue).
+ *
+ * Pixels are numbered row-major over [Bl+Bu, h, w] (labelled images first), P of them.
+ * Class membership is one uint32 bitmask per pixel (C <= 32); "blocks" are runs of 256
+ * pixels (u2pl_contra_num_blocks).  Feature tensors [N, D, h, w] are addressed by element
+ * strides: element (n, d, pixel p) at n*sn + d*sd + p*sp  (NCHW: sd = h*w, sp = 1;
+ * channels-last: sd = 1, sp = D).
+ * ---------------------------------------------------------------------- */
+
+/* label[:, c] != 0  ->  bit c.   onehot [B, C, hw] int64, bits [B*hw].  (loss_helper.py:80-81 operands) */
+int u2pl_onehot_to_bits(const int64_t *onehot, int64_t B, int64_t C, int64_t hw, uint32_t *bits, void *stream);
+
+/* A8 fused: nearest-neighbour down-sampled low/high masks + class bitmask straight from the label
+ * maps and the full-resolution entropy -- what train_semi.py:408-465 builds through label_onehot
+ * (utils.py:50-59, scatter quirk Q8 reproduced) and four F.interpolate(mode="nearest") calls,
+ * without the two [B,C,H,W] fp32 one-hot temporaries.  label_l [Bl,H,W], label_u [Bu,H,W] int64;
+ * entropy [Bu,H,W]; outputs indexed over [(Bl+Bu), h, w]. */
+int u2pl_contra_prep_lowres(const int64_t *label_l, const int64_t *label_u, const float *entropy,
+                            const float *thresh, int lo_idx, int hi_idx,
+                            int64_t Bl, int64_t Bu, int64_t H, int64_t W, int64_t h, int64_t w,
+                            int64_t C, int64_t ignore, int negative_high_entropy,
+                            uint32_t *label_bits, float *low_mask, float *high_mask, void *stream);
+
+int64_t u2pl_contra_num_blocks(int64_t P);
+
+/* Loop 1 of the reference (loss_helper.py:103-154) for every class at once.
+ * bits3 [3][P]: 0 low-valid (:104), 1 anchor candidates (:108-110), 2 negative keys (:111-140).
+ * blockcnt/blockoff [3][C][nb]: per-block member counts and their exclusive scan per class;
+ * totals [3][C]: low_valid.sum() (:152), len(seg_feat_low_entropy_list[i]) (:175), #keys (:142). */
+int u2pl_contra_classify(const uint32_t *label_bits, const float *prob_l, const float *prob_u,
+                         const float *low_mask, const float *high_mask,
+                         int64_t Bl, int64_t Bu, int64_t C, int64_t hw,
+                         float current_class_threshold, float current_class_negative_threshold,
+                         int low_rank, int high_rank,
+                         uint32_t *bits3, uint32_t *blockcnt, uint32_t *blockoff, uint32_t *totals, void *stream);
+
+/* class prototypes: mean of rep_teacher rows over low-valid pixels (:119-123).
+ * partial: scratch [u2pl_contra_proto_parts()][C][D] fp32; proto [C][D] (NaN rows for empty classes). */
+int64_t u2pl_contra_proto_parts(void);
+int u2pl_contra_proto(const float *rep_teacher, int64_t sn, int64_t sd, int64_t sp,
+                      int64_t P, int64_t C, int64_t D, int64_t hw,
+                      const uint32_t *lv_bits, const uint32_t *lv_totals,
+                      float *partial, float *proto, void *stream);
+
+/* keys = rep_teacher[negative_mask] (:142) for all classes into packed [sum_c k_c, D], class-major,
+ * pixel order inside a class.  class_base [C] = exclusive scan of the key counts (device). */
+int u2pl_contra_pack_keys(const float *rep_teacher, int64_t sn, int64_t sd, int64_t sp,
+                          int64_t P, int64_t C, int64_t D, int64_t hw,
+                          const uint32_t *ng_bits, const uint32_t *blockoff_ng, const uint32_t *class_base,
+                          float *packed, void *stream);
+
+/* dequeue_and_enqueue (utils.py:28-47) on a device-resident ring buffer.  bank [rows][D];
+ * desc: ndesc x 5 uint32 {src_first_row, dst_row_base, dst_first_pos, capacity, count}: row r of the
+ * segment goes to bank[dst_row_base + (dst_first_pos + r) % capacity].  The FIFO arithmetic
+ * (newest queue_size rows survive) is host bookkeeping: u2pl_b200/bank.py. */
+int u2pl_bank_append(const float *src_rows, float *bank, int64_t D, const uint32_t *desc, int ndesc,
+                     int64_t max_count, void *stream);
+
+/* Loop 2 (:173-230) for all active classes in one launch: one warp per (class, query).
+ * act_class [nact]: list position j whose anchors/prototype are used (quirk Q1: the bank rows in
+ * neg_rows were sampled from class valid_classes[j]); a_ord [nact][nq]: anchor ordinals drawn by
+ * torch.randint on the host (:179-181); neg_rows [nact][nq][nneg]: physical bank rows (:194-197).
+ * Outputs: loss_q [nact*nq], grad_rows [nact*nq][D] (= d loss / d anchor row, already scaled by
+ * 1/(nq*valid_seg)), anchor_pix [nact*nq], loss (scalar) = sum_q CE_q / (nq*valid_seg)  (:228-233). */
+int u2pl_infonce_forward(const float *rep, int64_t sn, int64_t sd, int64_t sp,
+                         int64_t P, int64_t D, int64_t hw,
+                         const uint32_t *an_bits, const uint32_t *blockoff_an,
+                         const int32_t *act_class, const int32_t *a_ord, const int32_t *neg_rows,
+                         const float *proto, const float *bank,
+                         int nact, int nq, int nneg, float temperature, int valid_seg,
+                         float *loss_q, float *grad_rows, int32_t *anchor_pix, float *loss, void *stream);
+
+/* grad_rep[anchor pixel, :] += upstream * grad_rows (atomics: queries are sampled with replacement). */
+int u2pl_infonce_backward(const float *grad_rows, const int32_t *anchor_pix, int nrows,
+                          int64_t D, int64_t hw, int64_t sn, int64_t sd, int64_t sp,
+                          const float *upstream, float *grad_rep, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,19 @@ SIGNATURES = {
     "u2pl_ce_forward": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_size_t, _S]),
     "u2pl_ce_backward": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _S]),
     "u2pl_unsup_finalize": (c_int, [_P, _P, c_int64, _P, _P, _P, _S]),
+    "u2pl_onehot_to_bits": (c_int, [_P, c_int64, c_int64, c_int64, _P, _S]),
+    "u2pl_contra_prep_lowres": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                        c_int64, c_int64, c_int, _P, _P, _P, _S]),
+    "u2pl_contra_num_blocks": (c_int64, [c_int64]),
+    "u2pl_contra_classify": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_float, c_float,
+                                     c_int, c_int, _P, _P, _P, _P, _S]),
+    "u2pl_contra_proto_parts": (c_int64, []),
+    "u2pl_contra_proto": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _S]),
+    "u2pl_contra_pack_keys": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _S]),
+    "u2pl_bank_append": (c_int, [_P, _P, c_int64, _P, c_int, c_int64, _S]),
+    "u2pl_infonce_forward": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P,
+                                     c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _S]),
+    "u2pl_infonce_backward": (c_int, [_P, _P, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _S]),
 }
 
 _lib = None

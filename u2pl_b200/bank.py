@@ -1,0 +1,96 @@
+"""Device-resident class-wise memory bank (reference: train_semi.py:161-169 builds
+`memobank` / `queue_ptrlis` / `queue_size` as CPU lists; utils.py:28-47 appends to them).
+
+The reference keeps every bank as a CPU tensor, re-allocates it on every append and copies the
+whole bank host->device once per class per step (loss_helper.py:192, up to 665 MB/step).  Here
+all C banks live in ONE device tensor [sum(queue_size), D]; each class is a ring buffer
+(start, length) over its own row range, so `keep the newest queue_size rows` is pointer
+arithmetic and an append only writes the new rows.
+
+This file is host bookkeeping only (pure Python/numpy, unit-tested on CPU against the oracle's
+dequeue_and_enqueue); the row copies are u2pl_bank_append (csrc/contra.cu).
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class Ring:
+    cap: int            # queue_size[c]
+    row_base: int       # first row of this class inside the shared bank tensor
+    start: int = 0      # ring position of logical row 0
+    length: int = 0     # rows held (== memobank[c][0].shape[0] in the reference)
+    ptr: int = 0        # queue_ptrlis[c][0] in the reference (utils.py:36-45)
+
+
+def plan_append(ring, seg_counts, seg_src_first):
+    """FIFO arithmetic of utils.py:38-43 for one class.
+
+    seg_counts[r]    : keys contributed by rank r (rank order = reference's concat order, :21-32)
+    seg_src_first[r] : row of rank r's first key for this class inside the gathered key buffer
+    Returns (descriptors, total_new) and updates `ring`.  A descriptor is
+    (src_first_row, dst_row_base, dst_first_pos, capacity, count): source row i goes to
+    bank[dst_row_base + (dst_first_pos + i) % capacity]."""
+    k = int(sum(seg_counts))
+    total = ring.length + k
+    if total < ring.cap:                               # :42-43
+        drop_old, skip, new_len = 0, 0, total
+        ring.ptr = (ring.ptr + k) % ring.cap
+    else:                                              # :39-41  queue[0][-queue_size:]
+        drop_total = total - ring.cap
+        drop_old = min(drop_total, ring.length)
+        skip = drop_total - drop_old                   # oldest NEW rows that never make it in
+        new_len = ring.cap
+        ring.ptr = ring.cap
+    new_start = (ring.start + drop_old) % ring.cap
+    kept_old = ring.length - drop_old
+    descs = []
+    s = 0
+    for k_r, src in zip(seg_counts, seg_src_first):
+        k_r = int(k_r)
+        lo = max(s, skip)
+        if lo < s + k_r:
+            descs.append((int(src) + (lo - s), ring.row_base, (new_start + kept_old + (lo - skip)) % ring.cap,
+                          ring.cap, s + k_r - lo))
+        s += k_r
+    ring.start, ring.length = new_start, new_len
+    return descs, k
+
+
+def physical_rows(ring, logical_idx):
+    """Bank-tensor rows of logical indices (what `negative_feat[high_entropy_idx]` addresses, :197)."""
+    idx = np.asarray(logical_idx, dtype=np.int64)
+    return (ring.row_base + (ring.start + idx) % ring.cap).astype(np.int32)
+
+
+class DeviceBank:
+    """All class banks in one device tensor + per-class Ring state."""
+
+    def __init__(self, queue_size, dim, device):
+        import torch
+        self.dim = int(dim)
+        self.rings = []
+        base = 0
+        for cap in queue_size:
+            self.rings.append(Ring(cap=int(cap), row_base=base))
+            base += int(cap)
+        self.rows = torch.zeros((base, self.dim), dtype=torch.float32, device=device)
+
+    def length(self, c):
+        return self.rings[c].length
+
+    def materialize(self, c):
+        """Logical-order copy of bank c (what memobank[c][0] holds in the reference)."""
+        import torch
+        r = self.rings[c]
+        idx = (r.start + torch.arange(r.length, device=self.rows.device)) % r.cap + r.row_base
+        return self.rows[idx]
+
+    def load(self, c, rows):
+        """Adopt pre-existing rows (e.g. a bank the caller filled on the CPU)."""
+        r = self.rings[c]
+        n = min(int(rows.shape[0]), r.cap)
+        self.rows[r.row_base:r.row_base + n] = rows[-n:].to(self.rows.device, self.rows.dtype)
+        r.start, r.length = 0, n
+        r.ptr = r.cap if rows.shape[0] >= r.cap else n % r.cap

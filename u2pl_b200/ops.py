@@ -178,3 +178,44 @@ class _UnsupLoss(torch.autograd.Function):
 
 def unsup_loss(predict, target, percent, pred_teacher, ignore=255):
     return _UnsupLoss.apply(predict, target, float(percent), pred_teacher.detach(), ignore)
+
+
+# --------------------------------------------------------------------------- A8 helpers
+def label_onehot(inputs, num_segments, ignore=255):
+    """utils.py:50-59 with its scatter quirk (Q8): slot 0 = union of all images' classes (ignored
+    pixels count as class 0), cleared where image 0 is ignored; slots b > 0 all-zero.  Only the
+    unchanged reference driver calls this (train_semi.py:456-465); the fused step never builds the
+    [B,C,H,W] tensor (contra_prep_lowres)."""
+    _need_cuda(inputs)
+    B, H, W = inputs.shape
+    out = torch.zeros((B, num_segments, H, W), dtype=torch.float32, device=inputs.device)
+    t = torch.where(inputs == ignore, torch.zeros_like(inputs), inputs)
+    out[0].scatter_(0, t, 1.0)
+    out[0] *= (inputs[0] != ignore)
+    return out
+
+
+def contra_prep_lowres(label_l, label_u_aug, entropy, thresh, lo_idx, hi_idx, out_hw, num_classes,
+                       negative_high_entropy=True, ignore=255):
+    """Fused train_semi.py:408-465 -> (label_bits [P] int32, low_mask [Bl+Bu,1,h,w], high_mask [Bl+Bu,1,h,w])."""
+    _need_cuda(label_l, label_u_aug, entropy, thresh)
+    lib = _lib.load()
+    Bl, H, W = label_l.shape
+    Bu = label_u_aug.shape[0]
+    h, w = out_hw
+    P = (Bl + Bu) * h * w
+    dev = label_l.device
+    bits = torch.empty(P, dtype=torch.int32, device=dev)
+    low = torch.empty((Bl + Bu, 1, h, w), dtype=torch.float32, device=dev)
+    high = torch.empty((Bl + Bu, 1, h, w), dtype=torch.float32, device=dev)
+    label_l, label_u_aug, entropy = label_l.contiguous(), label_u_aug.contiguous(), entropy.contiguous()
+    assert label_l.dtype == torch.int64 and label_u_aug.dtype == torch.int64
+    rc = lib.u2pl_contra_prep_lowres(_p(label_l), _p(label_u_aug), _p(entropy), _p(thresh), int(lo_idx), int(hi_idx),
+                                     Bl, Bu, H, W, h, w, int(num_classes), int(ignore), int(bool(negative_high_entropy)),
+                                     _p(bits), _p(low), _p(high), _stream())
+    _lib.check(rc, "u2pl_contra_prep_lowres")
+    return bits, low, high
+
+
+def ohem_cross_entropy(pred, target, thresh, min_kept, ignore=255):
+    raise NotImplementedError("OHEM criterion (loss_helper.py:451-531, Cityscapes configs) is the next row to build")
