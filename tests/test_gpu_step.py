@@ -1,0 +1,100 @@
+"""GPU integration: u2pl_b200.step.SemiStep (fp32 network, dropout off) against the CPU restatement of the
+reference driver step (oracle/step_port.py) from identical weights, inputs and RNG seeds.
+The network runs through different conv libraries on the two sides (cuDNN fp32 vs MKL-DNN), so logits
+agree to ~1e-5 only; the three losses must then agree to 2e-3 relative (loose by design: this test
+checks the wiring -- order of operations, percent schedules, bank use, EMA -- not kernel numerics,
+which the kernel-level tests pin bit-exactly)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(C):
+    return {
+        "dataset": {"ignore_label": 255, "type": "pascal_semi"},
+        "trainer": {"epochs": 80, "sup_only_epoch": 0,
+                    "optimizer": {"type": "SGD", "kwargs": {"lr": 0.001, "momentum": 0.9, "weight_decay": 0.0001}},
+                    "unsupervised": {"drop_percent": 80, "apply_aug": "cutmix"},
+                    "contrastive": {"negative_high_entropy": True, "low_rank": 3, "high_rank": 20,
+                                    "current_class_threshold": 0.3, "current_class_negative_threshold": 1,
+                                    "low_entropy_threshold": 20, "num_negatives": 50, "num_queries": 256,
+                                    "temperature": 0.5}},
+        "criterion": {"type": "CELoss", "kwargs": {"use_weight": False}},
+        "net": {"num_classes": C, "sync_bn": False, "ema_decay": 0.99,
+                "encoder": {"type": "u2pl.models.resnet.resnet50",
+                            "kwargs": {"multi_grid": True, "zero_init_residual": True, "fpn": True,
+                                       "replace_stride_with_dilation": [False, True, True], "pretrained": False}},
+                "decoder": {"type": "u2pl.models.decoder.dec_deeplabv3_plus",
+                            "kwargs": {"inner_planes": 256, "dilations": [12, 24, 36]}}},
+    }
+
+
+def test_semi_step_matches_reference_step():
+    import u2pl_b200
+    u2pl_b200.install()
+    from u2pl.models.model_helper import ModelBuilder
+    from u2pl.utils.loss_helper import get_criterion
+    from u2pl.utils.lr_helper import get_optimizer
+    from u2pl_b200 import contra
+    from u2pl_b200.step import SemiStep
+    from oracle import model_port, step_port
+    import bench
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    C, crop, bl, bu = 21, 97, 2, 2
+    cfg = _cfg(C)
+    torch.manual_seed(3)
+    model = ModelBuilder(copy.deepcopy(cfg["net"]))
+    with torch.no_grad():
+        model.decoder.classifier[-1].weight.mul_(8.0)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.p = 0.0
+    teacher = copy.deepcopy(model)
+    s_state = model_port.state_from_module(model)
+    t_state = model_port.state_from_module(teacher)
+    ref = step_port.ReferenceStep(s_state, t_state, cfg, "resnet50")
+    ref.student.dropout_p = ref.teacher.dropout_p = 0.0
+
+    model.cuda()
+    teacher.cuda()
+    for p in teacher.parameters():
+        p.requires_grad = False
+    lr = 0.001
+    opt = get_optimizer([dict(params=model.encoder.parameters(), lr=lr),
+                         dict(params=model.decoder.parameters(), lr=lr * 10)], cfg["trainer"]["optimizer"])
+    memobank = [[torch.zeros(0, 256)] for _ in range(C)]
+    ptrs = [torch.zeros(1, dtype=torch.long) for _ in range(C)]
+    qsize = [30000] * C
+    qsize[0] = 50000
+    step = SemiStep(model, teacher, opt, get_criterion(cfg), cfg, memobank, ptrs, qsize, amp=False, channels_last=False)
+
+    got, want = [], []
+    for rnd, (seed_np, seed_t) in enumerate([(5, 6), (7, 8)]):
+        image_l, label_l, image_u = bench.synth_batch(100 + rnd, bl, bu, crop, C)
+        np.random.seed(seed_np)
+        torch.manual_seed(seed_t)
+        want.append(ref.step(image_l, label_l, image_u, 40, 4000 + rnd, 100))
+        np.random.seed(seed_np)
+        torch.manual_seed(seed_t)
+        losses = step(image_l.cuda(), label_l.cuda(), image_u.cuda(), 40, 4000 + rnd, 100)
+        got.append([float(x) for x in losses.cpu()])
+        assert step.last["new_keys"] is not None
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), (got, want)
+    assert want[1][2] > 0 and got[1][2] > 0            # the contrastive branch really ran in step 2
+    # teacher EMA + bank sizes track the reference
+    bank = contra.bank_for(memobank, qsize, 256, "cuda")
+    lens_ref = [m[0].shape[0] for m in ref.memobank]
+    lens = [bank.length(c) for c in range(C)]
+    assert sum(abs(a - b) for a, b in zip(lens, lens_ref)) <= max(2, sum(lens_ref) // 100), (lens, lens_ref)
+    k = "decoder.classifier.8.weight"
+    t_w = dict(teacher.named_parameters())[k].detach().cpu()
+    assert (t_w - ref.teacher.s[k].detach()).abs().max() <= 1e-4
+    contra.forget_banks()

@@ -143,18 +143,16 @@ def cross_entropy_mean(logits, target, ignore=255):
     return _CrossEntropyMean.apply(logits, target, ignore)
 
 
-class _UnsupLoss(torch.autograd.Function):
-    """compute_unsupervised_loss (loss_helper.py:30-48) as one fused chain:
-    entropy + percentile + partition (no_grad part) and masked CE (autograd part)."""
+class _UnsupCE(torch.autograd.Function):
+    """Masked-CE half of compute_unsupervised_loss (loss_helper.py:44-46) on an already partitioned
+    target: CE forward and the weight = B*H*W / #kept algebra, all without a host round trip."""
 
     @staticmethod
-    def forward(ctx, predict, target, percent, pred_teacher, ignore):
-        _need_cuda(predict, target, pred_teacher)
+    def forward(ctx, predict, target, n_kept, ignore):
+        _need_cuda(predict, target, n_kept)
         lib = _lib.load()
         predict = _f32c(predict)
         assert target.is_contiguous() and target.dtype == torch.int64
-        ent, thresh, _ = entropy_thresholds(pred_teacher, target, [percent], ignore)
-        n_kept, _ = partition_target_(ent, target, thresh, 0, ignore)         # mutates caller's tensor, like the reference
         nll, _ = _ce_forward(predict, target, ignore)
         loss = torch.empty((), dtype=torch.float32, device=predict.device)
         total = target.numel()
@@ -173,11 +171,23 @@ class _UnsupLoss(torch.autograd.Function):
         scale = torch.empty(1, dtype=torch.float32, device=predict.device)
         rc = lib.u2pl_unsup_finalize(_p(nll), _p(n_kept), ctx.total, _p(gout), None, _p(scale), _stream())
         _lib.check(rc, "u2pl_unsup_finalize(bwd)")
-        return _ce_backward(predict, target, ctx.ignore, scale), None, None, None, None
+        return _ce_backward(predict, target, ctx.ignore, scale), None, None, None
+
+
+def unsup_ce(predict, target_partitioned, n_kept, ignore=255):
+    return _UnsupCE.apply(predict, target_partitioned, n_kept, ignore)
+
+
+def unsup_loss_from_entropy(predict, target, ent, thresh, thresh_idx=0, ignore=255):
+    """Partition (rewrites `target` in place like loss_helper.py:43) + weighted masked CE."""
+    n_kept, _ = partition_target_(ent, target, thresh, int(thresh_idx), ignore)
+    return _UnsupCE.apply(predict, target, n_kept, ignore)
 
 
 def unsup_loss(predict, target, percent, pred_teacher, ignore=255):
-    return _UnsupLoss.apply(predict, target, float(percent), pred_teacher.detach(), ignore)
+    """compute_unsupervised_loss(predict, target, percent, pred_teacher) -- loss_helper.py:30-48."""
+    ent, thresh, _ = entropy_thresholds(pred_teacher.detach(), target, [float(percent)], ignore)
+    return unsup_loss_from_entropy(predict, target, ent, thresh, 0, ignore)
 
 
 # --------------------------------------------------------------------------- A8 helpers
