@@ -99,6 +99,19 @@ int u2pl_ce_forward(const float *logits, const int64_t *target, int64_t B, int64
 int u2pl_ce_backward(const float *logits, const int64_t *target, int64_t B, int64_t C, int64_t HW,
                      int64_t ignore, const float *scale, float *grad, void *stream);
 
+/* ------------------------------------------------------------------------
+ * A12  OHEM pixel selection (OhemCrossEntropy2dTensor.forward, loss_helper.py:502-531)
+ *   mask_prob = softmax(pred)[target]  (1 where target == ignore)
+ *   kth = min(N, min_kept)-th smallest mask_prob (radix select instead of the reference's full sort)
+ *   threshold = max(thresh, kth); kept = mask_prob <= threshold     (skipped if min_kept > #valid)
+ *   new_target = kept ? target : ignore        (the CE itself is u2pl_ce_forward / backward)
+ * kth_value (fp32) and n_valid (int64) are device outputs; workspace as u2pl_entropy_ws_bytes.
+ * ---------------------------------------------------------------------- */
+int u2pl_ohem_select(const float *logits, const int64_t *target, int64_t B, int64_t C, int64_t HW,
+                     int64_t ignore, float thresh, int64_t min_kept,
+                     int64_t *new_target, float *kth_value, int64_t *n_valid,
+                     void *ws, size_t ws_bytes, void *stream);
+
 /* unsup loss scalar of loss_helper.py:44-46 on device:
  *   loss = (total_pixels / n_kept) * (nll_sum / n_kept);   bwd_scale = upstream * total_pixels / n_kept^2
  * n_kept == 0 gives loss = NaN like the reference (0/0). upstream may be NULL (= 1). */

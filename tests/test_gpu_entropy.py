@@ -161,3 +161,30 @@ def test_full_size_v16_properties():
     xs = x.permute(0, 2, 3, 1).reshape(-1, C)[torch.from_numpy(idx).cuda()].cpu().numpy()      # [50000, C]
     ent_s = port.entropy(np.ascontiguousarray(xs.T[None]))[0]                                  # B=1, HW=50000
     assert np.array_equal(ent_s.view(np.uint32), e[idx].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["ohem_c19", "ohem_c19_kth"])
+def test_ohem_golden(golden, name):
+    """OHEM (loss_helper.py:502-531): kept set bit-exact vs the oracle, loss/grad vs oracle and reference."""
+    ops = _ops()
+    g = golden(name)
+    pred_np, target_np = g["pred"], g["target"].astype(np.int64)
+    pred = _dev(pred_np).requires_grad_(True)
+    loss = ops.ohem_cross_entropy(pred, _dev(target_np), float(g["thresh"]), int(g["min_kept"]))
+    loss.backward()
+    want, kept = port.ohem_ce(pred_np, target_np, float(g["thresh"]), int(g["min_kept"]))
+    new_target, kth, n_valid = ops.ohem_select(_dev(pred_np), _dev(target_np), float(g["thresh"]), int(g["min_kept"]))
+    assert np.array_equal(new_target.cpu().numpy() != 255, kept)                # bit-exact kept set
+    assert n_valid.item() == int((target_np != 255).sum())
+    assert abs(loss.item() - float(want)) <= 1e-5 and abs(loss.item() - float(g["loss"])) <= 1e-4
+    assert np.abs(pred.grad.cpu().numpy() - g["grad"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("C,min_kept", [(7, 50), (21, 100000), (19, 0), (21, 1)])
+def test_ohem_edge_cases(C, min_kept):
+    ops = _ops()
+    rng = np.random.default_rng(C + min_kept)
+    x, target = _rand_case(rng, 2, C, 31, 33, 0.3, scale=1.5)
+    new_target, _, _ = ops.ohem_select(_dev(x), _dev(target), 0.7, min_kept)
+    _, kept = port.ohem_ce(x, target, 0.7, min_kept)
+    assert np.array_equal(new_target.cpu().numpy() != 255, kept)

@@ -26,6 +26,7 @@ SIGNATURES = {
     "u2pl_ce_forward": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_size_t, _S]),
     "u2pl_ce_backward": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _S]),
     "u2pl_unsup_finalize": (c_int, [_P, _P, c_int64, _P, _P, _P, _S]),
+    "u2pl_ohem_select": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_float, c_int64, _P, _P, _P, _P, c_size_t, _S]),
     "u2pl_onehot_to_bits": (c_int, [_P, c_int64, c_int64, c_int64, _P, _S]),
     "u2pl_contra_prep_lowres": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                         c_int64, c_int64, c_int, _P, _P, _P, _S]),

@@ -14,7 +14,6 @@ STAMP = os.path.join(HERE, ".libu2pl_b200.stamp")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
-    "--fmad=false",          # the arithmetic contract spells out every fma (arith.cuh)
     "-Xptxas", "-v",
 ]
 

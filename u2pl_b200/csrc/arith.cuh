@@ -63,6 +63,56 @@ __device__ __forceinline__ float det_logf(float y)
     return __fmaf_rn(ef, kLn2, l);
 }
 
+
+// ---- packed (f32x2) forms: sm_100 issues two IEEE binary32 operations per instruction
+// (FFMA2 / FMUL2 / FADD2).  Every lane-half performs exactly the scalar sequence above, so the
+// results are bit-identical to det_expf / det_logf; only the issue-slot count halves.
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+
+__device__ __forceinline__ float2 det_expf2(float2 d)
+{
+    d.x = fmaxf(d.x, -87.0f);
+    d.y = fmaxf(d.y, -87.0f);
+    const float2 t  = __ffma2_rn(d, f2(kLog2e), f2(kMagic));
+    const float2 kf = __fadd2_rn(t, f2(-kMagic));
+    const float2 r  = __ffma2_rn(kf, f2(-kLn2), d);
+    float2 q = f2(0.0013933652080595493f);
+    q = __ffma2_rn(q, r, f2(0.008363181725144386f));
+    q = __ffma2_rn(q, r, f2(0.04166646674275398f));
+    q = __ffma2_rn(q, r, f2(0.16666576266288757f));
+    q = __ffma2_rn(q, r, f2(0.5f));
+    const float2 r2 = __fmul2_rn(r, r);
+    float2 p = __ffma2_rn(r2, q, r);
+    p = __fadd2_rn(p, f2(1.0f));
+    p.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+    p.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+    return p;
+}
+
+__device__ __forceinline__ float2 det_logf2(float2 y)
+{
+    const uint32_t ix = __float_as_uint(y.x), iy = __float_as_uint(y.y);
+    const int32_t ex = static_cast<int32_t>(ix - 0x3f3504f3u) >> 23;
+    const int32_t ey = static_cast<int32_t>(iy - 0x3f3504f3u) >> 23;
+    const float2 m = make_float2(__uint_as_float(ix - (static_cast<uint32_t>(ex) << 23)),
+                                 __uint_as_float(iy - (static_cast<uint32_t>(ey) << 23)));
+    const float2 ef = __fadd2_rn(make_float2(__uint_as_float(0x4B400000u + static_cast<uint32_t>(ex)),
+                                             __uint_as_float(0x4B400000u + static_cast<uint32_t>(ey))), f2(-kMagic));
+    const float2 f = __fadd2_rn(m, f2(-1.0f));
+    float2 R = f2(0.08507229387760162f);
+    R = __ffma2_rn(R, f, f2(-0.14198024570941925f));
+    R = __ffma2_rn(R, f, f2(0.1495114266872406f));
+    R = __ffma2_rn(R, f, f2(-0.16587895154953003f));
+    R = __ffma2_rn(R, f, f2(0.1996057629585266f));
+    R = __ffma2_rn(R, f, f2(-0.2500097155570984f));
+    R = __ffma2_rn(R, f, f2(0.33333972096443176f));
+    const float2 fsq = __fmul2_rn(f, f);
+    const float2 u  = __ffma2_rn(f, R, f2(-0.5f));
+    const float2 tt = __fmul2_rn(fsq, u);
+    const float2 l  = __fadd2_rn(f, tt);
+    return __ffma2_rn(ef, f2(kLn2), l);
+}
+
 // Order-preserving float -> uint32 key (total order, -0 < +0).
 __device__ __forceinline__ uint32_t float_key(float v)
 {

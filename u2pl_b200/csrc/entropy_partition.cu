@@ -13,6 +13,7 @@
 //
 // HBM-bound by design: K1 moves (4C + 8 + 4 + 4) B/pixel, K7 moves 4+8+8+1 B/pixel,
 // K3/K5 re-read 4 B/pixel of keys out of the 126 MB L2.  Nothing synchronises the host.
+#include <algorithm>
 #include "arith.cuh"
 #include "common.cuh"
 
@@ -32,58 +33,87 @@ struct SelState {
     uint32_t pad[3];
 };
 
-struct Percents { float q[kMaxQ]; };
+struct Percents { float q[kMaxQ]; int use_rank; uint32_t rank; };   // use_rank: one explicit order statistic instead
 
 // ------------------------------------------------------------------ K1
+// Two pixels per thread, packed f32x2 arithmetic (x = pixel A, y = pixel B).
 template <int C>
-__device__ __forceinline__ float entropy_of(float (&v)[C])
+__device__ __forceinline__ float2 entropy_of2(float2 (&v)[C])
 {
-    float m = v[0];
+    float2 m = v[0];
 #pragma unroll
-    for (int c = 1; c < C; ++c) m = fmaxf(m, v[c]);
-    float S = 0.0f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        v[c] = det_expf(__fadd_rn(v[c], -m));
-        S = __fadd_rn(S, v[c]);
-    }
-    const float rinv = __fdiv_rn(1.0f, S);
-    float acc = 0.0f;
+    for (int c = 1; c < C; ++c) { m.x = fmaxf(m.x, v[c].x); m.y = fmaxf(m.y, v[c].y); }
+    const float2 nm = make_float2(-m.x, -m.y);
+    float2 S = f2(0.0f);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const float p = __fmul_rn(v[c], rinv);
-        const float l = det_logf(__fadd_rn(p, 1e-10f));
-        acc = __fmaf_rn(p, l, acc);
+        v[c] = det_expf2(__fadd2_rn(v[c], nm));
+        S = __fadd2_rn(S, v[c]);
     }
-    return -acc;
+    const float2 rinv = make_float2(__fdiv_rn(1.0f, S.x), __fdiv_rn(1.0f, S.y));
+    float2 acc = f2(0.0f);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float2 p = __fmul2_rn(v[c], rinv);
+        const float2 l = det_logf2(__fadd2_rn(p, f2(1e-10f)));
+        acc = __ffma2_rn(p, l, acc);
+    }
+    return make_float2(-acc.x, -acc.y);
 }
 
+// warp-aggregated shared-memory histogram increment: lanes that hit the same bin elect one leader
+// (real teacher logits put most pixels into a handful of bins; plain atomics would serialise 32-way)
+__device__ __forceinline__ void hist_add(uint32_t *sh, uint32_t bin)
+{
+    const uint32_t m = __activemask();
+    const uint32_t peers = __match_any_sync(m, bin);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bin], __popc(peers));
+}
+
+constexpr int kEntThreads = 256;
+constexpr int kEntTile = 2 * kEntThreads;          // pixels per block iteration
+
 template <int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kEntThreads)
 entropy_hist_kernel(const float *__restrict__ logits, const int64_t *__restrict__ target,
                     uint32_t HW, uint32_t N, int64_t ignore,
                     float *__restrict__ ent, uint32_t *__restrict__ keys,
                     uint32_t *__restrict__ hist1)
 {
     __shared__ uint32_t sh[kBins1];
-    for (int j = threadIdx.x; j < kBins1; j += 256) sh[j] = 0;
+    for (int j = threadIdx.x; j < kBins1; j += kEntThreads) sh[j] = 0;
     __syncthreads();
-    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < N; i += gridDim.x * 256u) {
-        const uint32_t b = i / HW, p = i - b * HW;
-        const float *x = logits + static_cast<size_t>(b) * C * HW + p;
-        float v[C];
+    for (uint32_t base = blockIdx.x * kEntTile; base < N; base += gridDim.x * kEntTile) {
+        // thread handles pixels iA and iB = iA + 256: both loads of a warp are fully coalesced
+        const uint32_t iA = base + threadIdx.x, iB = iA + kEntThreads;
+        const bool hasA = iA < N, hasB = iB < N;
+        const uint32_t jA = hasA ? iA : N - 1, jB = hasB ? iB : N - 1;
+        const uint32_t bA = jA / HW, pA = jA - bA * HW, bB = jB / HW, pB = jB - bB * HW;
+        const float *xA = logits + static_cast<size_t>(bA) * C * HW + pA;
+        const float *xB = logits + static_cast<size_t>(bB) * C * HW + pB;
+        float2 v[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
-        const int64_t t = __ldg(target + i);
-        const float h = entropy_of<C>(v);
-        ent[i] = h;
-        const bool valid = (t != ignore);
-        const uint32_t key = valid ? float_key(h) : kInvalidKey;
-        keys[i] = key;
-        if (valid) atomicAdd(&sh[key >> 20], 1u);
+        for (int c = 0; c < C; ++c)
+            v[c] = make_float2(__ldg(xA + static_cast<size_t>(c) * HW), __ldg(xB + static_cast<size_t>(c) * HW));
+        const int64_t tA = __ldg(target + jA), tB = __ldg(target + jB);
+        const float2 h = entropy_of2<C>(v);
+        if (hasA) {
+            ent[iA] = h.x;
+            const bool valid = (tA != ignore);
+            const uint32_t key = valid ? float_key(h.x) : kInvalidKey;
+            keys[iA] = key;
+            if (valid) hist_add(sh, key >> 20);
+        }
+        if (hasB) {
+            ent[iB] = h.y;
+            const bool valid = (tB != ignore);
+            const uint32_t key = valid ? float_key(h.y) : kInvalidKey;
+            keys[iB] = key;
+            if (valid) hist_add(sh, key >> 20);
+        }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < kBins1; j += 256)
+    for (int j = threadIdx.x; j < kBins1; j += kEntThreads)
         if (sh[j]) atomicAdd(&hist1[j], sh[j]);
 }
 
@@ -118,7 +148,7 @@ entropy_hist_kernel_anyC(const float *__restrict__ logits, const int64_t *__rest
         const bool valid = (__ldg(target + i) != ignore);
         const uint32_t key = valid ? float_key(h) : kInvalidKey;
         keys[i] = key;
-        if (valid) atomicAdd(&sh[key >> 20], 1u);
+        if (valid) hist_add(sh, key >> 20);
     }
     __syncthreads();
     for (int j = threadIdx.x; j < kBins1; j += 256)
@@ -156,7 +186,12 @@ select1_kernel(const uint32_t *__restrict__ hist1, SelState *__restrict__ st, Pe
         st->n = n;
         // numpy 2.x: q32 = q / float32(100); v = float32(n-1) * q32  (all binary32)
         const float nm1 = __uint2float_rn(n ? n - 1u : 0u);
-        for (int j = 0; j < nq; ++j) {
+        if (pc.use_rank) {                                  // OHEM: the k-th smallest value itself (no interpolation)
+            const uint32_t r = n ? min(pc.rank, n - 1u) : 0u;
+            st->gamma[0] = 0.0f;
+            s_rank[0] = s_rank[1] = r;
+        }
+        for (int j = 0; j < (pc.use_rank ? 0 : nq); ++j) {
             const float q32 = __fdiv_rn(pc.q[j], 100.0f);
             const float v = __fmul_rn(nm1, q32);
             const float fl = floorf(v);
@@ -212,10 +247,22 @@ hist_refine_kernel(const uint32_t *__restrict__ keys, uint32_t N,
                 const uint32_t key = kk[e];
                 if (key == kInvalidKey) continue;
                 const uint32_t hi = key >> kMatchShift;
-                const uint32_t bin = (key >> kBinShift) & (kBinsR - 1);
+                uint32_t mt = 0;                                   // targets whose prefix this key extends
 #pragma unroll
-                for (int t = 0; t < kMaxT; ++t)
-                    if (t < T && hi == pre[t]) atomicAdd(&sh[t * kBinsR + bin], 1u);
+                for (int t = 0; t < kMaxT; ++t) mt |= (t < T && hi == pre[t]) ? (1u << t) : 0u;
+                if (mt) {
+                    const uint32_t bin = (key >> kBinShift) & (kBinsR - 1);
+                    const uint32_t am = __activemask();
+                    const uint32_t peers = __match_any_sync(am, (mt << 10) | bin);
+                    if ((threadIdx.x & 31) == __ffs(peers) - 1) {
+                        const uint32_t cnt = __popc(peers);
+                        while (mt) {
+                            const int t = __ffs(mt) - 1;
+                            mt &= mt - 1;
+                            atomicAdd(&sh[t * kBinsR + bin], cnt);
+                        }
+                    }
+                }
             }
         }
         if (blockIdx.x == 0 && threadIdx.x < (N & 3u)) {
@@ -247,7 +294,7 @@ select_refine_kernel(const uint32_t *__restrict__ hist, SelState *__restrict__ s
     if (n == 0) {
         if (FINAL && tid == 0) {
             for (int j = 0; j < nq; ++j) thresh[j] = __uint_as_float(0x7fc00000u);
-            *n_valid = 0;
+            if (n_valid) *n_valid = 0;
         }
         return;
     }
@@ -284,7 +331,7 @@ select_refine_kernel(const uint32_t *__restrict__ hist, SelState *__restrict__ s
             if (g >= 0.5f) r = __fadd_rn(b, -__fmul_rn(d, __fadd_rn(1.0f, -g)));
             thresh[j] = r;
         }
-        *n_valid = static_cast<int64_t>(n);
+        if (n_valid) *n_valid = static_cast<int64_t>(n);
     }
 }
 
@@ -328,6 +375,107 @@ entropy_masks_kernel(const float *__restrict__ ent, const int64_t *__restrict__ 
         const bool valid = (__ldg(target + s) != ignore);
         if (out_low) out_low[j] = (valid && e <= tl) ? 1.0f : 0.0f;
         if (out_high) out_high[j] = (valid && e >= thh) ? 1.0f : 0.0f;
+    }
+}
+
+
+// ------------------------------------------------------------------ OHEM (loss_helper.py:502-531)
+// mask_prob = softmax(pred)[target] (1.0 where target == ignore), computed under the arithmetic
+// contract because the kept set is cut by an order statistic of it (:520-524).
+template <int C>
+__global__ void __launch_bounds__(256)
+ohem_prob_hist_kernel(const float *__restrict__ logits, const int64_t *__restrict__ target,
+                      uint32_t HW, uint32_t N, int64_t ignore, uint32_t *__restrict__ keys,
+                      uint32_t *__restrict__ hist1, unsigned long long *__restrict__ n_valid)
+{
+    __shared__ uint32_t sh[kBins1];
+    for (int j = threadIdx.x; j < kBins1; j += 256) sh[j] = 0;
+    __syncthreads();
+    int nv = 0;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < N; i += gridDim.x * 256u) {
+        const int64_t t = __ldg(target + i);
+        float mp = 1.0f;                                            // :516 masked_fill_(~valid, 1)
+        if (t != ignore) {
+            ++nv;
+            const uint32_t b = i / HW, p = i - b * HW;
+            const float *x = logits + static_cast<size_t>(b) * C * HW + p;
+            float v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
+            float m = v[0];
+#pragma unroll
+            for (int c = 1; c < C; ++c) m = fmaxf(m, v[c]);
+            float S = 0.0f, et = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float e = det_expf(__fadd_rn(v[c], -m));
+                S = __fadd_rn(S, e);
+                et = (c == static_cast<int>(t)) ? e : et;
+            }
+            mp = __fmul_rn(et, __fdiv_rn(1.0f, S));
+        }
+        const uint32_t key = float_key(mp);
+        keys[i] = key;
+        hist_add(sh, key >> 20);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < kBins1; j += 256)
+        if (sh[j]) atomicAdd(&hist1[j], sh[j]);
+    nv = warp_sum_i(nv);
+    if ((threadIdx.x & 31) == 0 && nv) atomicAdd(n_valid, static_cast<unsigned long long>(nv));
+}
+
+__global__ void __launch_bounds__(256)
+ohem_prob_hist_kernel_anyC(const float *__restrict__ logits, const int64_t *__restrict__ target, uint32_t C,
+                           uint32_t HW, uint32_t N, int64_t ignore, uint32_t *__restrict__ keys,
+                           uint32_t *__restrict__ hist1, unsigned long long *__restrict__ n_valid)
+{
+    __shared__ uint32_t sh[kBins1];
+    for (int j = threadIdx.x; j < kBins1; j += 256) sh[j] = 0;
+    __syncthreads();
+    int nv = 0;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < N; i += gridDim.x * 256u) {
+        const int64_t t = __ldg(target + i);
+        float mp = 1.0f;
+        if (t != ignore) {
+            ++nv;
+            const uint32_t b = i / HW, p = i - b * HW;
+            const float *x = logits + static_cast<size_t>(b) * C * HW + p;
+            float m = __ldg(x);
+            for (uint32_t c = 1; c < C; ++c) m = fmaxf(m, __ldg(x + static_cast<size_t>(c) * HW));
+            float S = 0.0f, et = 0.0f;
+            for (uint32_t c = 0; c < C; ++c) {
+                const float e = det_expf(__fadd_rn(__ldg(x + static_cast<size_t>(c) * HW), -m));
+                S = __fadd_rn(S, e);
+                et = (c == static_cast<uint32_t>(t)) ? e : et;
+            }
+            mp = __fmul_rn(et, __fdiv_rn(1.0f, S));
+        }
+        const uint32_t key = float_key(mp);
+        keys[i] = key;
+        hist_add(sh, key >> 20);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < kBins1; j += 256)
+        if (sh[j]) atomicAdd(&hist1[j], sh[j]);
+    nv = warp_sum_i(nv);
+    if ((threadIdx.x & 31) == 0 && nv) atomicAdd(n_valid, static_cast<unsigned long long>(nv));
+}
+
+__global__ void __launch_bounds__(256)
+ohem_partition_kernel(const uint32_t *__restrict__ keys, const int64_t *__restrict__ target, uint32_t N,
+                      int64_t ignore, float thresh, long long min_kept, const float *__restrict__ kth,
+                      const unsigned long long *__restrict__ n_valid, int64_t *__restrict__ new_target)
+{
+    const long long nv = static_cast<long long>(*n_valid);
+    const bool filter = !(min_kept > nv) && nv > 0 && min_kept > 0;       // :512-519
+    const float k = __ldg(kth);
+    const float threshold = (k > thresh) ? k : thresh;                      // :518,522-523
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < N; i += gridDim.x * 256u) {
+        const int64_t t = __ldg(target + i);
+        bool keep = (t != ignore);
+        if (keep && filter) keep = key_float(__ldg(keys + i)) <= threshold; // :524-526
+        new_target[i] = keep ? t : ignore;                                   // :528
     }
 }
 
@@ -375,8 +523,8 @@ template <int C>
 static void launch_entropy(const float *logits, const int64_t *target, uint32_t HW, uint32_t N,
                            int64_t ignore, float *ent, const EntropyWs &w, cudaStream_t s)
 {
-    const int grid = grid_for(reinterpret_cast<const void *>(entropy_hist_kernel<C>), 256, 0, N);
-    entropy_hist_kernel<C><<<grid, 256, 0, s>>>(logits, target, HW, N, ignore, ent, w.keys, w.hist1);
+    const int grid = grid_for(reinterpret_cast<const void *>(entropy_hist_kernel<C>), kEntThreads, 0, N, 2);
+    entropy_hist_kernel<C><<<grid, kEntThreads, 0, s>>>(logits, target, HW, N, ignore, ent, w.keys, w.hist1);
 }
 
 }  // namespace u2pl
@@ -405,6 +553,7 @@ extern "C" int u2pl_entropy_thresholds(const float *logits, const int64_t *targe
     cudaError_t e = cudaMemsetAsync(w.hist1, 0, w.zero_bytes, s);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
     Percents pc;
+    pc.use_rank = 0; pc.rank = 0;
     for (int j = 0; j < kMaxQ; ++j) pc.q[j] = (j < nq) ? h_percents[j] : 0.0f;
 
     switch (C) {
@@ -453,4 +602,41 @@ extern "C" int u2pl_entropy_masks(const float *entropy, const int64_t *target, c
     entropy_masks_kernel<<<grid, 256, 0, s>>>(entropy, target, idx, static_cast<uint32_t>(n_out), ignore, thresh,
                                               lo_idx, hi_idx, out_low, out_high);
     return check_launch("entropy_masks");
+}
+
+extern "C" int u2pl_ohem_select(const float *logits, const int64_t *target, int64_t B, int64_t C, int64_t HW,
+                                int64_t ignore, float thresh, int64_t min_kept,
+                                int64_t *new_target, float *kth_value, int64_t *n_valid,
+                                void *ws, size_t ws_bytes, void *stream)
+{
+    if (B <= 0 || C <= 0 || HW <= 0 || B * HW >= (1LL << 31)) return bad_arg("ohem_select: bad shape");
+    if (ws_bytes < ws_layout(B * HW, nullptr, nullptr)) { set_error("ohem_select: workspace too small"); return U2PL_E_WS_SMALL; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t N = static_cast<uint32_t>(B * HW), hw = static_cast<uint32_t>(HW);
+    EntropyWs w;
+    ws_layout(B * HW, ws, &w);
+    cudaError_t e = cudaMemsetAsync(w.hist1, 0, w.zero_bytes, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(n_valid, 0, sizeof(int64_t), s);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
+    unsigned long long *nv = reinterpret_cast<unsigned long long *>(n_valid);
+    const int grid = static_cast<int>(std::min<long long>((static_cast<long long>(N) + 255) / 256, 148 * 6));
+    switch (C) {
+        case 19: ohem_prob_hist_kernel<19><<<grid, 256, 0, s>>>(logits, target, hw, N, ignore, w.keys, w.hist1, nv); break;
+        case 21: ohem_prob_hist_kernel<21><<<grid, 256, 0, s>>>(logits, target, hw, N, ignore, w.keys, w.hist1, nv); break;
+        default: ohem_prob_hist_kernel_anyC<<<grid, 256, 0, s>>>(logits, target, static_cast<uint32_t>(C), hw, N, ignore, w.keys, w.hist1, nv);
+    }
+    Percents pc;
+    for (int j = 0; j < kMaxQ; ++j) pc.q[j] = 0.0f;
+    pc.use_rank = 1;
+    const long long k = std::min<long long>(static_cast<long long>(N), std::max<long long>(min_kept, 1)) - 1;   // :521
+    pc.rank = static_cast<uint32_t>(k);
+    select1_kernel<<<1, 256, 0, s>>>(w.hist1, w.st, pc, 1);
+    const size_t smem = 2 * kBinsR * 4;
+    const int g2 = grid_for(reinterpret_cast<const void *>(hist_refine_kernel<2>), 256, smem, N, 4);
+    hist_refine_kernel<2><<<g2, 256, smem, s>>>(w.keys, N, w.st, w.hist2, 2);
+    select_refine_kernel<false><<<1, 1024, 0, s>>>(w.hist2, w.st, 1, kth_value, nullptr);
+    hist_refine_kernel<3><<<g2, 256, smem, s>>>(w.keys, N, w.st, w.hist3, 2);
+    select_refine_kernel<true><<<1, 1024, 0, s>>>(w.hist3, w.st, 1, kth_value, nullptr);
+    ohem_partition_kernel<<<grid, 256, 0, s>>>(w.keys, target, N, ignore, thresh, static_cast<long long>(min_kept), kth_value, nv, new_target);
+    return check_launch("ohem_select", 7);
 }

@@ -227,5 +227,25 @@ def contra_prep_lowres(label_l, label_u_aug, entropy, thresh, lo_idx, hi_idx, ou
     return bits, low, high
 
 
+def ohem_select(pred, target, thresh, min_kept, ignore=255):
+    """Kept-pixel target of OhemCrossEntropy2dTensor (loss_helper.py:502-529).  Returns
+    (new_target int64, kth_value fp32 device scalar, n_valid int64 device scalar)."""
+    _need_cuda(pred, target)
+    lib = _lib.load()
+    pred = _f32c(pred.detach())
+    target = target.contiguous()
+    B, C, H, W = pred.shape
+    new_target = torch.empty_like(target)
+    kth = torch.empty((), dtype=torch.float32, device=pred.device)
+    n_valid = torch.empty((), dtype=torch.int64, device=pred.device)
+    ws = _workspace("entropy", lib.u2pl_entropy_ws_bytes(B, H * W), pred.device)
+    rc = lib.u2pl_ohem_select(_p(pred), _p(target), B, C, H * W, int(ignore), float(thresh), int(min_kept),
+                              _p(new_target), _p(kth), _p(n_valid), _p(ws), ws.numel(), _stream())
+    _lib.check(rc, "u2pl_ohem_select")
+    return new_target, kth, n_valid
+
+
 def ohem_cross_entropy(pred, target, thresh, min_kept, ignore=255):
-    raise NotImplementedError("OHEM criterion (loss_helper.py:451-531, Cityscapes configs) is the next row to build")
+    """OhemCrossEntropy2dTensor.forward (loss_helper.py:502-531): mean CE over the kept pixels."""
+    new_target, _, _ = ohem_select(pred, target, thresh, min_kept, ignore)
+    return cross_entropy_mean(pred, new_target, ignore)
