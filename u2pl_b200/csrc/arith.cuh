@@ -64,53 +64,36 @@ __device__ __forceinline__ float det_logf(float y)
 }
 
 
-// ---- packed (f32x2) forms: sm_100 issues two IEEE binary32 operations per instruction
-// (FFMA2 / FMUL2 / FADD2).  Every lane-half performs exactly the scalar sequence above, so the
-// results are bit-identical to det_expf / det_logf; only the issue-slot count halves.
-__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+// NOTE on packed f32x2 (FFMA2/FADD2/FMUL2, sm_100): a two-pixels-per-thread variant of the entropy
+// arithmetic was built and measured in round 1.  (1) It gave no throughput: FFMA2 issues at half the
+// FFMA rate on B200, and the kernel is bound by the integer (ALU-pipe) half of exp/log anyway.
+// (2) With nvcc/ptxas 12.9 the unrolled 21-class loop produced wrong .x (LO-half) results for
+// det_logf2 while the same function was correct in isolation (tools/cu/entropy_probe2.cu dumps the
+// stages) -- a miscompile or a missing hazard on register pairs fed by integer ops.  The scalar
+// form below is therefore the only one shipped.
 
-__device__ __forceinline__ float2 det_expf2(float2 d)
+// Scalar per-pixel entropy under the contract (C register-resident logits in v[]).
+template <int C>
+__device__ __forceinline__ float entropy_of(float (&v)[C])
 {
-    d.x = fmaxf(d.x, -87.0f);
-    d.y = fmaxf(d.y, -87.0f);
-    const float2 t  = __ffma2_rn(d, f2(kLog2e), f2(kMagic));
-    const float2 kf = __fadd2_rn(t, f2(-kMagic));
-    const float2 r  = __ffma2_rn(kf, f2(-kLn2), d);
-    float2 q = f2(0.0013933652080595493f);
-    q = __ffma2_rn(q, r, f2(0.008363181725144386f));
-    q = __ffma2_rn(q, r, f2(0.04166646674275398f));
-    q = __ffma2_rn(q, r, f2(0.16666576266288757f));
-    q = __ffma2_rn(q, r, f2(0.5f));
-    const float2 r2 = __fmul2_rn(r, r);
-    float2 p = __ffma2_rn(r2, q, r);
-    p = __fadd2_rn(p, f2(1.0f));
-    p.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
-    p.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
-    return p;
-}
-
-__device__ __forceinline__ float2 det_logf2(float2 y)
-{
-    const uint32_t ix = __float_as_uint(y.x), iy = __float_as_uint(y.y);
-    const int32_t ex = static_cast<int32_t>(ix - 0x3f3504f3u) >> 23;
-    const int32_t ey = static_cast<int32_t>(iy - 0x3f3504f3u) >> 23;
-    const float2 m = make_float2(__uint_as_float(ix - (static_cast<uint32_t>(ex) << 23)),
-                                 __uint_as_float(iy - (static_cast<uint32_t>(ey) << 23)));
-    const float2 ef = __fadd2_rn(make_float2(__uint_as_float(0x4B400000u + static_cast<uint32_t>(ex)),
-                                             __uint_as_float(0x4B400000u + static_cast<uint32_t>(ey))), f2(-kMagic));
-    const float2 f = __fadd2_rn(m, f2(-1.0f));
-    float2 R = f2(0.08507229387760162f);
-    R = __ffma2_rn(R, f, f2(-0.14198024570941925f));
-    R = __ffma2_rn(R, f, f2(0.1495114266872406f));
-    R = __ffma2_rn(R, f, f2(-0.16587895154953003f));
-    R = __ffma2_rn(R, f, f2(0.1996057629585266f));
-    R = __ffma2_rn(R, f, f2(-0.2500097155570984f));
-    R = __ffma2_rn(R, f, f2(0.33333972096443176f));
-    const float2 fsq = __fmul2_rn(f, f);
-    const float2 u  = __ffma2_rn(f, R, f2(-0.5f));
-    const float2 tt = __fmul2_rn(fsq, u);
-    const float2 l  = __fadd2_rn(f, tt);
-    return __ffma2_rn(ef, f2(kLn2), l);
+    float m = v[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmaxf(m, v[c]);
+    float S = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        v[c] = det_expf(__fadd_rn(v[c], -m));
+        S = __fadd_rn(S, v[c]);
+    }
+    const float rinv = __fdiv_rn(1.0f, S);
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float p = __fmul_rn(v[c], rinv);
+        const float l = det_logf(__fadd_rn(p, 1e-10f));
+        acc = __fmaf_rn(p, l, acc);
+    }
+    return -acc;
 }
 
 // Order-preserving float -> uint32 key (total order, -0 < +0).

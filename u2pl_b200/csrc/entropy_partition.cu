@@ -36,31 +36,6 @@ struct SelState {
 struct Percents { float q[kMaxQ]; int use_rank; uint32_t rank; };   // use_rank: one explicit order statistic instead
 
 // ------------------------------------------------------------------ K1
-// Two pixels per thread, packed f32x2 arithmetic (x = pixel A, y = pixel B).
-template <int C>
-__device__ __forceinline__ float2 entropy_of2(float2 (&v)[C])
-{
-    float2 m = v[0];
-#pragma unroll
-    for (int c = 1; c < C; ++c) { m.x = fmaxf(m.x, v[c].x); m.y = fmaxf(m.y, v[c].y); }
-    const float2 nm = make_float2(-m.x, -m.y);
-    float2 S = f2(0.0f);
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        v[c] = det_expf2(__fadd2_rn(v[c], nm));
-        S = __fadd2_rn(S, v[c]);
-    }
-    const float2 rinv = make_float2(__fdiv_rn(1.0f, S.x), __fdiv_rn(1.0f, S.y));
-    float2 acc = f2(0.0f);
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        const float2 p = __fmul2_rn(v[c], rinv);
-        const float2 l = det_logf2(__fadd2_rn(p, f2(1e-10f)));
-        acc = __ffma2_rn(p, l, acc);
-    }
-    return make_float2(-acc.x, -acc.y);
-}
-
 // warp-aggregated shared-memory histogram increment: lanes that hit the same bin elect one leader
 // (real teacher logits put most pixels into a handful of bins; plain atomics would serialise 32-way)
 __device__ __forceinline__ void hist_add(uint32_t *sh, uint32_t bin)
@@ -71,7 +46,6 @@ __device__ __forceinline__ void hist_add(uint32_t *sh, uint32_t bin)
 }
 
 constexpr int kEntThreads = 256;
-constexpr int kEntTile = 2 * kEntThreads;          // pixels per block iteration
 
 template <int C>
 __global__ void __launch_bounds__(kEntThreads)
@@ -83,34 +57,19 @@ entropy_hist_kernel(const float *__restrict__ logits, const int64_t *__restrict_
     __shared__ uint32_t sh[kBins1];
     for (int j = threadIdx.x; j < kBins1; j += kEntThreads) sh[j] = 0;
     __syncthreads();
-    for (uint32_t base = blockIdx.x * kEntTile; base < N; base += gridDim.x * kEntTile) {
-        // thread handles pixels iA and iB = iA + 256: both loads of a warp are fully coalesced
-        const uint32_t iA = base + threadIdx.x, iB = iA + kEntThreads;
-        const bool hasA = iA < N, hasB = iB < N;
-        const uint32_t jA = hasA ? iA : N - 1, jB = hasB ? iB : N - 1;
-        const uint32_t bA = jA / HW, pA = jA - bA * HW, bB = jB / HW, pB = jB - bB * HW;
-        const float *xA = logits + static_cast<size_t>(bA) * C * HW + pA;
-        const float *xB = logits + static_cast<size_t>(bB) * C * HW + pB;
-        float2 v[C];
+    for (uint32_t i = blockIdx.x * kEntThreads + threadIdx.x; i < N; i += gridDim.x * kEntThreads) {
+        const uint32_t b = i / HW, p = i - b * HW;
+        const float *x = logits + static_cast<size_t>(b) * C * HW + p;
+        float v[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-            v[c] = make_float2(__ldg(xA + static_cast<size_t>(c) * HW), __ldg(xB + static_cast<size_t>(c) * HW));
-        const int64_t tA = __ldg(target + jA), tB = __ldg(target + jB);
-        const float2 h = entropy_of2<C>(v);
-        if (hasA) {
-            ent[iA] = h.x;
-            const bool valid = (tA != ignore);
-            const uint32_t key = valid ? float_key(h.x) : kInvalidKey;
-            keys[iA] = key;
-            if (valid) hist_add(sh, key >> 20);
-        }
-        if (hasB) {
-            ent[iB] = h.y;
-            const bool valid = (tB != ignore);
-            const uint32_t key = valid ? float_key(h.y) : kInvalidKey;
-            keys[iB] = key;
-            if (valid) hist_add(sh, key >> 20);
-        }
+        for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);     // C coalesced loads in flight
+        const int64_t t = __ldg(target + i);
+        const float h = entropy_of<C>(v);
+        ent[i] = h;
+        const bool valid = (t != ignore);
+        const uint32_t key = valid ? float_key(h) : kInvalidKey;
+        keys[i] = key;
+        if (valid) hist_add(sh, key >> 20);
     }
     __syncthreads();
     for (int j = threadIdx.x; j < kBins1; j += kEntThreads)
@@ -523,7 +482,7 @@ template <int C>
 static void launch_entropy(const float *logits, const int64_t *target, uint32_t HW, uint32_t N,
                            int64_t ignore, float *ent, const EntropyWs &w, cudaStream_t s)
 {
-    const int grid = grid_for(reinterpret_cast<const void *>(entropy_hist_kernel<C>), kEntThreads, 0, N, 2);
+    const int grid = grid_for(reinterpret_cast<const void *>(entropy_hist_kernel<C>), kEntThreads, 0, N);
     entropy_hist_kernel<C><<<grid, kEntThreads, 0, s>>>(logits, target, HW, N, ignore, ent, w.keys, w.hist1);
 }
 
