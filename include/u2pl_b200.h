@@ -198,6 +198,36 @@ int u2pl_infonce_backward(const float *grad_rows, const int32_t *anchor_pix, int
                           int64_t D, int64_t hw, int64_t sn, int64_t sd, int64_t sp,
                           const float *upstream, float *grad_rep, void *stream);
 
+/* ------------------------------------------------------------------------
+ * A1/A2  batch normalisation (+ReLU, +residual) on channels-last bf16 activations
+ * replaces: nn.BatchNorm2d / nn.SyncBatchNorm + nn.ReLU + residual add as used in
+ *           u2pl/models/resnet.py:120-140, base.py:22-76, decoder.py:57-100.
+ * x, y, residual, dy, dx, dres: [M, C] bf16 row-major (= NHWC with M = N*H*W), 16-byte aligned;
+ * C % 8 == 0, C/8 a power of two, C <= 2048.  Statistics, gamma/beta, running stats: fp32.
+ *   u2pl_bn_stats            sums[0][c] = sum_m x, sums[1][c] = sum_m x^2   (partial: scratch
+ *                            [u2pl_bn_parts()][2][C]); all-reduce `sums` across ranks for SyncBN
+ *   u2pl_bn_finalize         mean, invstd (biased var + eps), running-stat update (unbiased var,
+ *                            momentum; pass NULL to skip), scale = gamma*invstd, shift = beta - mean*scale
+ *   u2pl_bn_fold             eval mode: scale/shift from the running statistics
+ *   u2pl_bn_apply            y = [relu]( x*scale + shift [+ residual] )
+ *   u2pl_bn_backward_reduce  sums[0] = sum g, sums[1] = sum g*xhat,  g = dy * (y > 0)  (y NULL: no ReLU)
+ *   u2pl_bn_backward_elemt   dx = gamma*invstd*(g - sums[0]/count - xhat*sums[1]/count); dres = g (NULL: skip)
+ * ---------------------------------------------------------------------- */
+int64_t u2pl_bn_parts(void);
+int u2pl_bn_stats(const void *x, int64_t M, int64_t C, float *partial, float *sums, void *stream);
+int u2pl_bn_finalize(const float *sums, int64_t C, double count, const float *gamma, const float *beta,
+                     float *running_mean, float *running_var, float momentum, float eps,
+                     float *mean, float *invstd, float *scale, float *shift, void *stream);
+int u2pl_bn_fold(int64_t C, const float *gamma, const float *beta, const float *running_mean,
+                 const float *running_var, float eps, float *scale, float *shift, void *stream);
+int u2pl_bn_apply(const void *x, const void *residual, const float *scale, const float *shift,
+                  int64_t M, int64_t C, int relu, void *y, void *stream);
+int u2pl_bn_backward_reduce(const void *dy, const void *x, const void *y, const float *mean, const float *invstd,
+                            int64_t M, int64_t C, float *partial, float *sums, void *stream);
+int u2pl_bn_backward_elemt(const void *dy, const void *x, const void *y, const float *mean, const float *invstd,
+                           const float *gamma, const float *sums, double count, int64_t M, int64_t C,
+                           void *dx, void *dres, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

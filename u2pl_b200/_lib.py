@@ -4,7 +4,7 @@ There is no fallback: if the library is missing or a call fails, this raises.
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libu2pl_b200.so")
@@ -40,6 +40,13 @@ SIGNATURES = {
     "u2pl_infonce_forward": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P,
                                      c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _S]),
     "u2pl_infonce_backward": (c_int, [_P, _P, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _S]),
+    "u2pl_bn_parts": (c_int64, []),
+    "u2pl_bn_stats": (c_int, [_P, c_int64, c_int64, _P, _P, _S]),
+    "u2pl_bn_finalize": (c_int, [_P, c_int64, c_double, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _S]),
+    "u2pl_bn_fold": (c_int, [c_int64, _P, _P, _P, _P, c_float, _P, _P, _S]),
+    "u2pl_bn_apply": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, _P, _S]),
+    "u2pl_bn_backward_reduce": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _S]),
+    "u2pl_bn_backward_elemt": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_double, c_int64, c_int64, _P, _P, _S]),
 }
 
 _lib = None

@@ -1,0 +1,195 @@
+"""Fused network blocks used by the model mirror on the GPU.
+
+* `bn_act(x, bn, relu, residual)`: BatchNorm (+ReLU, +residual add) for channels-last bf16
+  activations through the kernels of csrc/bn.cu (train and eval mode, SyncBN aware).  It reads the
+  parameters / running statistics of the nn.BatchNorm2d / nn.SyncBatchNorm module it is given, so
+  the module tree, state_dict keys and parameter order stay exactly the reference's
+  (resnet.py:93-140, base.py:11-100, decoder.py:45-142).
+* `run_sequential(seq, x)`: walks an nn.Sequential and fuses every (norm, ReLU) pair it finds.
+* `DilatedConv2d`: nn.Conv2d whose weight gradient for large dilations is computed as nine cropped
+  GEMMs.  cuDNN 9 picks `wgrad_alg0_engine_NHWC` (~43 TFLOP/s, 30 ms per layer per step on B200)
+  for the three ASPP convolutions (2048 -> 256, dilation 12/24/36); the GEMM form also skips the
+  taps' zero-padding region, which is most of the window at dilation 24/36 on a 65x65 map.
+
+Selection rule: the fused path is taken for CUDA bf16 channels-last tensors (what the step runs
+under autocast); fp32 tensors (CPU model-parity tests, `--fp32` runs) go through the nn.Modules.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .ops import _p, _stream
+
+ENABLED = {"bn": True, "wgrad": True}
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _is_cl_bf16(x):
+    return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def _bn_ok(x, bn):
+    C = x.shape[1]
+    return (ENABLED["bn"] and _is_cl_bf16(x) and isinstance(bn, (nn.BatchNorm2d, nn.SyncBatchNorm))
+            and C % 8 == 0 and C <= 2048 and 256 % (C // 8) == 0 and bn.momentum is not None
+            and bn.track_running_stats)
+
+
+def _scratch(dev, C):
+    lib = _lib.load()
+    parts = int(lib.u2pl_bn_parts())
+    return torch.empty((parts, 2, C), dtype=torch.float32, device=dev), torch.empty((2, C), dtype=torch.float32, device=dev)
+
+
+class _BNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, bn, relu, sync):
+        lib = _lib.load()
+        N, C, H, W = x.shape
+        M = N * H * W
+        dev = x.device
+        scale = torch.empty(C, dtype=torch.float32, device=dev)
+        shift = torch.empty(C, dtype=torch.float32, device=dev)
+        training = bn.training
+        count = float(M)
+        if training:
+            partial, sums = _scratch(dev, C)
+            _lib.check(lib.u2pl_bn_stats(_p(x), M, C, _p(partial), _p(sums), _stream()), "u2pl_bn_stats")
+            if sync:                                   # SyncBN: global sums; every rank holds the same number of
+                dist.all_reduce(sums)                  # pixels (same per-GPU batch and crop, as in the reference configs)
+                count = float(M) * _world()
+            mean = torch.empty(C, dtype=torch.float32, device=dev)
+            invstd = torch.empty(C, dtype=torch.float32, device=dev)
+            _lib.check(lib.u2pl_bn_finalize(_p(sums), C, ctypes.c_double(count), _p(weight), _p(bias),
+                                            _p(bn.running_mean), _p(bn.running_var), float(bn.momentum), float(bn.eps),
+                                            _p(mean), _p(invstd), _p(scale), _p(shift), _stream()), "u2pl_bn_finalize")
+            bn.num_batches_tracked.add_(1)
+        else:
+            mean = invstd = None
+            _lib.check(lib.u2pl_bn_fold(C, _p(weight), _p(bias), _p(bn.running_mean), _p(bn.running_var), float(bn.eps),
+                                        _p(scale), _p(shift), _stream()), "u2pl_bn_fold")
+        y = torch.empty_like(x)                        # preserves channels-last
+        _lib.check(lib.u2pl_bn_apply(_p(x), _p(residual), _p(scale), _p(shift), M, C, int(relu), _p(y), _stream()),
+                   "u2pl_bn_apply")
+        if training and any(ctx.needs_input_grad):
+            ctx.save_for_backward(x, y if relu else None, weight, mean, invstd)
+            ctx.meta = (M, C, count, sync, residual is not None, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, y, weight, mean, invstd = ctx.saved_tensors
+        M, C, count, sync, has_res, relu = ctx.meta
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dev = x.device
+        partial, sums = _scratch(dev, C)
+        _lib.check(lib.u2pl_bn_backward_reduce(_p(dy), _p(x), _p(y), _p(mean), _p(invstd), M, C, _p(partial), _p(sums),
+                                               _stream()), "u2pl_bn_backward_reduce")
+        dweight, dbias = sums[1].clone(), sums[0].clone()            # local sums = this rank's parameter gradients
+        if sync:
+            dist.all_reduce(sums)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_res else None
+        _lib.check(lib.u2pl_bn_backward_elemt(_p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(weight), _p(sums),
+                                              ctypes.c_double(count), M, C, _p(dx), _p(dres), _stream()),
+                   "u2pl_bn_backward_elemt")
+        return dx, dweight, dbias, dres, None, None, None
+
+
+def bn_act(x, bn, relu=None, residual=None):
+    """relu: an nn.ReLU module (or True) to fuse, or None.  residual: tensor added before the ReLU."""
+    if _bn_ok(x, bn) and (residual is None or _is_cl_bf16(residual)):
+        sync = isinstance(bn, nn.SyncBatchNorm) and bn.training and _world() > 1
+        return _BNAct.apply(x, bn.weight, bn.bias, residual, bn, relu is not None and relu is not False, sync)
+    y = bn(x)
+    if residual is not None:
+        y = y + residual
+    if relu is None or relu is False:
+        return y
+    return relu(y) if isinstance(relu, nn.Module) else F.relu(y)
+
+
+def run_sequential(seq, x):
+    """nn.Sequential.forward with (norm, ReLU) pairs fused."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, (nn.BatchNorm2d, nn.SyncBatchNorm)):
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if isinstance(nxt, nn.ReLU):
+                x = bn_act(x, m, nxt)
+                i += 2
+                continue
+            x = bn_act(x, m, None)
+        else:
+            x = m(x)
+        i += 1
+    return x
+
+
+# ----------------------------------------------------------------------------- dilated conv
+class _DilatedConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, dilation):
+        ctx.save_for_backward(x, w)
+        ctx.dilation = dilation
+        return F.conv2d(x, w, None, 1, dilation, dilation)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w = ctx.saved_tensors
+        d = ctx.dilation
+        gout = gout.contiguous(memory_format=torch.channels_last)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.ops.aten.convolution_backward(gout, x, w, None, [1, 1], [d, d], [d, d], False, [0, 0], 1,
+                                                     [True, False, False])[0]
+        dw = None
+        if ctx.needs_input_grad[1]:
+            N, Ci, H, W = x.shape
+            Co = w.shape[0]
+            xh = x.permute(0, 2, 3, 1)                   # NHWC views (no copies: both are channels-last)
+            gh = gout.permute(0, 2, 3, 1)
+            dw = torch.zeros((Co, 3, 3, Ci), dtype=torch.float32, device=x.device)
+            for ky in range(3):
+                oy = (ky - 1) * d                        # input row = output row + oy
+                y0, y1 = max(0, -oy), min(H, H - oy)
+                if y1 <= y0:
+                    continue
+                for kx in range(3):
+                    ox = (kx - 1) * d
+                    x0, x1 = max(0, -ox), min(W, W - ox)
+                    if x1 <= x0:
+                        continue
+                    g = gh[:, y0:y1, x0:x1, :].reshape(-1, Co)                       # cropped to the overlap:
+                    a = xh[:, y0 + oy:y1 + oy, x0 + ox:x1 + ox, :].reshape(-1, Ci)   # zero padding contributes nothing
+                    dw[:, ky, kx, :] = torch.mm(g.t(), a).float()
+            dw = dw.permute(0, 3, 1, 2).to(w.dtype)
+        return dx, dw, None
+
+
+class DilatedConv2d(nn.Conv2d):
+    """Same parameters / state_dict as nn.Conv2d; GEMM-based weight gradient for 3x3, stride 1,
+    padding == dilation >= 8 on CUDA bf16 channels-last inputs."""
+
+    def forward(self, x):
+        d = self.dilation[0]
+        fast = (ENABLED["wgrad"] and x.is_cuda and self.kernel_size == (3, 3) and self.stride == (1, 1)
+                and self.padding == (d, d) and self.dilation == (d, d) and d >= 8 and self.groups == 1
+                and self.bias is None and torch.is_autocast_enabled() and torch.is_grad_enabled())
+        if not fast:
+            return super().forward(x)
+        xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wb = self.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        with torch.autocast("cuda", enabled=False):
+            return _DilatedConvFn.apply(xb, wb, d)

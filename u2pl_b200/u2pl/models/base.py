@@ -4,6 +4,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from u2pl_b200.fused import DilatedConv2d, run_sequential
+
 
 def get_syncbn():
     # reference base.py:6-8
@@ -17,7 +19,8 @@ def _norm(sync_bn):
 def _conv_bn_relu(cin, cout, k, dilation, norm, pool=False):
     pad = 0 if k == 1 else dilation
     layers = [nn.AdaptiveAvgPool2d((1, 1))] if pool else []
-    layers += [nn.Conv2d(cin, cout, kernel_size=k, padding=pad, dilation=dilation, bias=False),
+    conv = DilatedConv2d if (k == 3 and dilation > 1) else nn.Conv2d      # same parameters, faster weight gradient
+    layers += [conv(cin, cout, kernel_size=k, padding=pad, dilation=dilation, bias=False),
                norm(cout), nn.ReLU(inplace=True)]
     return nn.Sequential(*layers)
 
@@ -40,5 +43,6 @@ class ASPP(nn.Module):
 
     def forward(self, x):
         h, w = x.shape[-2:]
-        pooled = F.interpolate(self.conv1(x), size=(h, w), mode="bilinear", align_corners=True)
-        return torch.cat((pooled, self.conv2(x), self.conv3(x), self.conv4(x), self.conv5(x)), 1)
+        pooled = F.interpolate(self.conv1(x), size=(h, w), mode="bilinear", align_corners=True)   # 1x1 map: BN stays ATen
+        branches = [run_sequential(b, x) for b in (self.conv2, self.conv3, self.conv4, self.conv5)]
+        return torch.cat([pooled] + branches, 1)

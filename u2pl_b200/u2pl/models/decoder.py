@@ -4,6 +4,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from u2pl_b200.fused import run_sequential
+
 from .base import ASPP, _norm
 
 
@@ -21,7 +23,7 @@ class dec_deeplabv3(nn.Module):
                                   nn.Conv2d(256, num_classes, kernel_size=1, stride=1, padding=0, bias=True))
 
     def forward(self, x):
-        return self.head(self.aspp(x))
+        return run_sequential(self.head, self.aspp(x))
 
 
 class dec_deeplabv3_plus(nn.Module):
@@ -44,13 +46,13 @@ class dec_deeplabv3_plus(nn.Module):
 
     def forward(self, x):
         x1, _, _, x4 = x
-        deep = self.head(self.aspp(x4))
-        low = self.low_conv(x1)
+        deep = run_sequential(self.head, self.aspp(x4))
+        low = run_sequential(self.low_conv, x1)
         deep = F.interpolate(deep, size=low.shape[-2:], mode="bilinear", align_corners=True)
         feat = torch.cat((low, deep), dim=1)
-        out = {"pred": self.classifier(feat)}
+        out = {"pred": run_sequential(self.classifier, feat)}
         if self.rep_head:
-            out["rep"] = self.representation(feat)
+            out["rep"] = run_sequential(self.representation, feat)
         return out
 
 
@@ -62,4 +64,4 @@ class Aux_Module(nn.Module):
                                  nn.Conv2d(256, num_classes, kernel_size=1, stride=1, padding=0, bias=True))
 
     def forward(self, x):
-        return self.aux(x)
+        return run_sequential(self.aux, x)

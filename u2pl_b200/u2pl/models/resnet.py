@@ -4,6 +4,8 @@ sequence, so a state_dict or a torch seed produces the same weights as the refer
 import torch
 import torch.nn as nn
 
+from u2pl_b200.fused import bn_act, run_sequential
+
 from .base import _norm
 
 __all__ = ["ResNet", "resnet18", "resnet34", "resnet50", "resnet101", "resnet152"]
@@ -40,10 +42,9 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        y = self.relu(self.bn1(self.conv1(x)))
-        y = self.bn2(self.conv2(y))
-        y += x if self.downsample is None else self.downsample(x)
-        return self.relu(y)
+        y = bn_act(self.conv1(x), self.bn1, self.relu)
+        identity = x if self.downsample is None else run_sequential(self.downsample, x)
+        return bn_act(self.conv2(y), self.bn2, self.relu, residual=identity)
 
 
 class Bottleneck(nn.Module):
@@ -64,11 +65,10 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        y = self.relu(self.bn1(self.conv1(x)))
-        y = self.relu(self.bn2(self.conv2(y)))
-        y = self.bn3(self.conv3(y))
-        y += x if self.downsample is None else self.downsample(x)
-        return self.relu(y)
+        y = bn_act(self.conv1(x), self.bn1, self.relu)
+        y = bn_act(self.conv2(y), self.bn2, self.relu)
+        identity = x if self.downsample is None else run_sequential(self.downsample, x)
+        return bn_act(self.conv3(y), self.bn3, self.relu, residual=identity)      # relu(bn3(.) + identity)
 
 
 class ResNet(nn.Module):
@@ -134,7 +134,7 @@ class ResNet(nn.Module):
         return nn.Sequential(*stack)
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(bn_act(run_sequential(self.conv1, x), self.bn1, self.relu))
         x1 = self.layer1(x)
         x2 = self.layer2(x1)
         x3 = self.layer3(x2)
