@@ -91,7 +91,10 @@ def test_dilated_conv_weight_grad(d):
 
 
 def test_model_bf16_fused_close_to_fp32():
-    """Whole mirror network: fused bf16 path vs its own fp32 module path (same weights), train mode, dropout off."""
+    """Whole mirror network: fused bf16 path vs its own fp32 module path (same weights).
+    eval mode: full outputs.  train mode: encoder features and gradients (the ASPP image-pool branch
+    batch-normalises N values per channel at 1x1 resolution -- with N=4 its output sign is decided by
+    rounding noise, so full train-mode outputs are not comparable across precisions)."""
     import copy
     import u2pl_b200
     u2pl_b200.install()
@@ -101,25 +104,33 @@ def test_model_bf16_fused_close_to_fp32():
                        "kwargs": {"multi_grid": True, "zero_init_residual": False, "fpn": True,
                                   "replace_stride_with_dilation": [False, True, True], "pretrained": False}},
            "decoder": {"type": "u2pl.models.decoder.dec_deeplabv3_plus", "kwargs": {"inner_planes": 256, "dilations": [12, 24, 36]}}}
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
     m32 = ModelBuilder(copy.deepcopy(net)).cuda()
-    for mod in m32.modules():
-        if isinstance(mod, nn.Dropout2d):
-            mod.p = 0.0
     mbf = copy.deepcopy(m32).to(memory_format=torch.channels_last)
-    x = torch.randn(2, 3, 97, 97, device="cuda")
-    out32 = m32(x)
+    x = torch.randn(4, 3, 97, 97, device="cuda")
+    # ---- train mode, encoder only
+    f32 = m32.encoder(x)
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        outbf = mbf(_cl(x))
-    for k in ("pred", "rep"):
-        rel = (outbf[k].float() - out32[k]).abs().max() / out32[k].abs().max()
-        assert rel <= 0.08, (k, float(rel))
-    (out32["pred"].float().mean() + out32["rep"].float().mean()).backward()
-    (outbf["pred"].float().mean() + outbf["rep"].float().mean()).backward()
+        fbf = mbf.encoder(_cl(x))
+    for a, b in zip(fbf, f32):
+        assert (a.float() - b).norm() <= 0.05 * b.norm()
+    sum(t.float().pow(2).mean() for t in f32).backward()
+    sum(t.float().pow(2).mean() for t in fbf).backward()
     p32, pbf = dict(m32.named_parameters()), dict(mbf.named_parameters())
-    for name in ("decoder.classifier.0.weight", "decoder.aspp.conv4.0.weight", "encoder.layer3.2.conv2.weight", "encoder.layer1.0.bn1.weight"):
+    for name in ("encoder.layer4.2.conv2.weight", "encoder.layer3.2.conv2.weight", "encoder.layer1.0.bn1.weight",
+                 "encoder.conv1.0.weight", "encoder.layer2.0.downsample.0.weight"):
         a, b = pbf[name].grad.float(), p32[name].grad
-        assert (a - b).norm() <= 0.15 * b.norm() + 1e-6, name
-    rm32 = dict(m32.named_buffers())["encoder.layer2.1.bn2.running_mean"]
-    rmbf = dict(mbf.named_buffers())["encoder.layer2.1.bn2.running_mean"]
-    assert (rm32 - rmbf).abs().max() <= 0.02 * max(1e-3, rm32.abs().max().item()) + 5e-3
+        assert (a - b).norm() <= 0.15 * b.norm() + 1e-7, (name, float((a - b).norm() / b.norm()))
+    rm32 = dict(m32.named_buffers())["encoder.layer2.1.bn2.running_var"]
+    rmbf = dict(mbf.named_buffers())["encoder.layer2.1.bn2.running_var"]
+    assert (rm32 - rmbf).abs().max() <= 0.03 * rm32.abs().max().item()
+    # ---- eval mode, whole network (running statistics folded into scale/shift)
+    m32.eval(); mbf.eval()
+    with torch.no_grad():
+        out32 = m32(x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outbf = mbf(_cl(x))
+    for k in ("pred", "rep"):
+        assert (outbf[k].float() - out32[k]).norm() <= 0.05 * out32[k].norm(), k

@@ -61,7 +61,10 @@ class SemiStep:
 
     @staticmethod
     def _up(t, size):
-        return F.interpolate(t.float(), size, mode="bilinear", align_corners=True)
+        # low-res logits leave the network channels-last; convert the small tensor (22 MB) to NCHW before
+        # the x4 up-sampling so the 354 MB full-resolution tensors reach the loss kernels in the layout the
+        # reference API defines (no hidden full-res transposes later)
+        return F.interpolate(t.float().contiguous(), size, mode="bilinear", align_corners=True)
 
     # ------------------------------------------------------------------ the step
     def __call__(self, image_l, label_l, image_u, epoch, i_iter, len_loader):
@@ -113,7 +116,7 @@ class SemiStep:
             teacher.train()
             with torch.no_grad():
                 out_t = self._net(teacher, torch.cat((image_l, image_u_aug)))
-                pred_all_teacher, rep_all_teacher = out_t["pred"].float(), out_t["rep"]
+                pred_all_teacher, rep_all_teacher = out_t["pred"].float().contiguous(), out_t["rep"]
                 prob_all_teacher = F.softmax(pred_all_teacher, dim=1)
                 pred_u_large_teacher = self._up(pred_all_teacher[num_labeled:], (h, w))
             # ---- unsupervised + contrastive losses, one entropy pass (:376-519)
