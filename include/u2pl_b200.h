@@ -226,7 +226,7 @@ int u2pl_bn_backward_reduce(const void *dy, const void *x, const void *y, const 
                             int64_t M, int64_t C, float *partial, float *sums, void *stream);
 int u2pl_bn_backward_elemt(const void *dy, const void *x, const void *y, const float *mean, const float *invstd,
                            const float *gamma, const float *sums, double count, int64_t M, int64_t C,
-                           void *dx, void *dres, void *stream);
+                           float *coef /* scratch [3][C] */, void *dx, void *dres, void *stream);
 
 #ifdef __cplusplus
 }

@@ -46,7 +46,7 @@ SIGNATURES = {
     "u2pl_bn_fold": (c_int, [c_int64, _P, _P, _P, _P, c_float, _P, _P, _S]),
     "u2pl_bn_apply": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, _P, _S]),
     "u2pl_bn_backward_reduce": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _S]),
-    "u2pl_bn_backward_elemt": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_double, c_int64, c_int64, _P, _P, _S]),
+    "u2pl_bn_backward_elemt": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_double, c_int64, c_int64, _P, _P, _P, _S]),
 }
 
 _lib = None

@@ -98,15 +98,25 @@ bn_stats_partial_kernel(const uint4 *__restrict__ x, long long M, int C, float *
     reduce_slots_store(s, q, tpr, C, out, out + C);
 }
 
-// sums[2][C] = sum over blocks of partial[b][2][C]   (double accumulation, fixed order)
+// sums[2][C] = sum over blocks of partial[b][2][C]   (double accumulation, fixed order).
+// 32 consecutive columns x 8 part-slices per block: every load is a coalesced 128 B row segment and
+// the serial chain is nparts/8 long.
 __global__ void __launch_bounds__(256)
 bn_reduce_kernel(const float *__restrict__ partial, int nparts, int C2, float *__restrict__ sums)
 {
-    const int j = blockIdx.x * 256 + threadIdx.x;
-    if (j >= C2) return;
+    __shared__ double sm[8][32];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31), sl = threadIdx.x >> 5;
     double a = 0.0;
-    for (int b = 0; b < nparts; ++b) a += static_cast<double>(partial[static_cast<size_t>(b) * C2 + j]);
-    sums[j] = static_cast<float>(a);
+    if (col < C2)
+        for (int b = sl; b < nparts; b += 8) a += static_cast<double>(__ldg(partial + static_cast<size_t>(b) * C2 + col));
+    sm[sl][threadIdx.x & 31] = a;
+    __syncthreads();
+    if (sl == 0 && col < C2) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+        sums[col] = static_cast<float>(t);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -207,17 +217,32 @@ bn_bwd_partial_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x,
     reduce_slots_store(s1, s2, tpr, C, out, out + C);
 }
 
+// dx = gamma*invstd*(g - s1/n - xhat*s2/n) folded into dx = A*g + B*x + D per channel:
+//   A = gamma*invstd,  B = -gamma*invstd^2*s2/n,  D = -A*s1/n - B*mean
+__global__ void __launch_bounds__(256)
+bn_bwd_coef_kernel(const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
+                   const float *__restrict__ sums, float inv_count, int C, float *__restrict__ coef)
+{
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    const float is = invstd[c], ga = gamma ? gamma[c] : 1.0f;
+    const float A = ga * is, B = -ga * is * is * sums[C + c] * inv_count;
+    coef[c] = A;
+    coef[C + c] = B;
+    coef[2 * C + c] = -A * sums[c] * inv_count - B * mean[c];
+}
+
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_elemt_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, const uint4 *__restrict__ y,
-                    const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
-                    const float *__restrict__ sums, float inv_count, long long nvec, int C,
-                    uint4 *__restrict__ dx, uint4 *__restrict__ dres)
+                    const float *__restrict__ coef, long long nvec, int C, uint4 *__restrict__ dx, uint4 *__restrict__ dres)
 {
     const int tpr = C >> 3;
+    const float4 *cA = reinterpret_cast<const float4 *>(coef), *cB = reinterpret_cast<const float4 *>(coef + C),
+                 *cD = reinterpret_cast<const float4 *>(coef + 2 * C);
     for (long long i = static_cast<long long>(blockIdx.x) * kBnThreads + threadIdx.x; i < nvec;
          i += static_cast<long long>(gridDim.x) * kBnThreads) {
-        const int c0 = static_cast<int>(i % tpr) * 8;
-        float g[8], xv[8], o[8];
+        const int cv = static_cast<int>(i % tpr) * 2;
+        float g[8], xv[8], o[8], A[8], B[8], D[8];
         unpack8(__ldg(dy + i), g);
         unpack8(__ldg(x + i), xv);
         if (y) {
@@ -226,12 +251,11 @@ bn_bwd_elemt_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, c
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.0f ? g[j] : 0.0f;
         }
+        *reinterpret_cast<float4 *>(A) = __ldg(cA + cv); *reinterpret_cast<float4 *>(A + 4) = __ldg(cA + cv + 1);
+        *reinterpret_cast<float4 *>(B) = __ldg(cB + cv); *reinterpret_cast<float4 *>(B + 4) = __ldg(cB + cv + 1);
+        *reinterpret_cast<float4 *>(D) = __ldg(cD + cv); *reinterpret_cast<float4 *>(D + 4) = __ldg(cD + cv + 1);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float is = __ldg(invstd + c0 + j), xh = (xv[j] - __ldg(mean + c0 + j)) * is;
-            const float ga = gamma ? __ldg(gamma + c0 + j) : 1.0f;
-            o[j] = ga * is * (g[j] - __ldg(sums + c0 + j) * inv_count - xh * __ldg(sums + C + c0 + j) * inv_count);
-        }
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], g[j], fmaf(B[j], xv[j], D[j]));
         dx[i] = pack8(o);
         if (dres) dres[i] = pack8(g);
     }
@@ -252,15 +276,17 @@ static bool bn_shape_ok(long long M, long long C) { return M > 0 && C >= 8 && C 
 
 using namespace u2pl;
 
-extern "C" int64_t u2pl_bn_parts(void) { return 148 * 4; }
+constexpr int kBnParts = 148 * 2;
+
+extern "C" int64_t u2pl_bn_parts(void) { return kBnParts; }
 
 extern "C" int u2pl_bn_stats(const void *x, int64_t M, int64_t C, float *partial, float *sums, void *stream)
 {
     if (!bn_shape_ok(M, C)) return bad_arg("bn_stats: need C % 8 == 0, C/8 a divisor of 256, C <= 2048");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int parts = 148 * 4;
+    const int parts = kBnParts;
     bn_stats_partial_kernel<<<parts, kBnThreads, 0, s>>>(static_cast<const uint4 *>(x), M, static_cast<int>(C), partial);
-    bn_reduce_kernel<<<static_cast<int>((2 * C + 255) / 256), 256, 0, s>>>(partial, parts, static_cast<int>(2 * C), sums);
+    bn_reduce_kernel<<<static_cast<int>((2 * C + 31) / 32), 256, 0, s>>>(partial, parts, static_cast<int>(2 * C), sums);
     return check_launch("bn_stats", 2);
 }
 
@@ -297,21 +323,24 @@ extern "C" int u2pl_bn_backward_reduce(const void *dy, const void *x, const void
 {
     if (!bn_shape_ok(M, C)) return bad_arg("bn_backward_reduce: unsupported channel count");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int parts = 148 * 4;
+    const int parts = kBnParts;
     bn_bwd_partial_kernel<<<parts, kBnThreads, 0, s>>>(static_cast<const uint4 *>(dy), static_cast<const uint4 *>(x),
                                                         static_cast<const uint4 *>(y), mean, invstd, M, static_cast<int>(C), partial);
-    bn_reduce_kernel<<<static_cast<int>((2 * C + 255) / 256), 256, 0, s>>>(partial, parts, static_cast<int>(2 * C), sums);
+    bn_reduce_kernel<<<static_cast<int>((2 * C + 31) / 32), 256, 0, s>>>(partial, parts, static_cast<int>(2 * C), sums);
     return check_launch("bn_backward_reduce", 2);
 }
 
 extern "C" int u2pl_bn_backward_elemt(const void *dy, const void *x, const void *y, const float *mean, const float *invstd,
                                       const float *gamma, const float *sums, double count, int64_t M, int64_t C,
-                                      void *dx, void *dres, void *stream)
+                                      float *coef, void *dx, void *dres, void *stream)
 {
     if (!bn_shape_ok(M, C)) return bad_arg("bn_backward_elemt: unsupported channel count");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long nvec = M * (C / 8);
-    bn_bwd_elemt_kernel<<<bn_grid(nvec), kBnThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4 *>(dy), static_cast<const uint4 *>(x), static_cast<const uint4 *>(y), mean, invstd, gamma, sums,
-        static_cast<float>(1.0 / count), nvec, static_cast<int>(C), static_cast<uint4 *>(dx), static_cast<uint4 *>(dres));
-    return check_launch("bn_backward_elemt");
+    bn_bwd_coef_kernel<<<static_cast<int>((C + 255) / 256), 256, 0, s>>>(mean, invstd, gamma, sums, static_cast<float>(1.0 / count),
+                                                                       static_cast<int>(C), coef);
+    bn_bwd_elemt_kernel<<<bn_grid(nvec), kBnThreads, 0, s>>>(static_cast<const uint4 *>(dy), static_cast<const uint4 *>(x),
+                                                             static_cast<const uint4 *>(y), coef, nvec, static_cast<int>(C),
+                                                             static_cast<uint4 *>(dx), static_cast<uint4 *>(dres));
+    return check_launch("bn_backward_elemt", 2);
 }

@@ -99,8 +99,9 @@ class _BNAct(torch.autograd.Function):
             dist.all_reduce(sums)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
+        coef = torch.empty((3, C), dtype=torch.float32, device=dev)
         _lib.check(lib.u2pl_bn_backward_elemt(_p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(weight), _p(sums),
-                                              ctypes.c_double(count), M, C, _p(dx), _p(dres), _stream()),
+                                              ctypes.c_double(count), M, C, _p(coef), _p(dx), _p(dres), _stream()),
                    "u2pl_bn_backward_elemt")
         return dx, dweight, dbias, dres, None, None, None
 
@@ -180,12 +181,13 @@ class _DilatedConvFn(torch.autograd.Function):
 
 class DilatedConv2d(nn.Conv2d):
     """Same parameters / state_dict as nn.Conv2d; GEMM-based weight gradient for 3x3, stride 1,
-    padding == dilation >= 8 on CUDA bf16 channels-last inputs."""
+    padding == dilation on CUDA bf16 channels-last inputs.  Used where cuDNN's heuristics fall back to
+    wgrad_alg0_engine (profiled: the three ASPP convs 2048->256 d=12/24/36 and the 1280->256 head conv)."""
 
     def forward(self, x):
         d = self.dilation[0]
         fast = (ENABLED["wgrad"] and x.is_cuda and self.kernel_size == (3, 3) and self.stride == (1, 1)
-                and self.padding == (d, d) and self.dilation == (d, d) and d >= 8 and self.groups == 1
+                and self.padding == (d, d) and self.dilation == (d, d) and self.groups == 1
                 and self.bias is None and torch.is_autocast_enabled() and torch.is_grad_enabled())
         if not fast:
             return super().forward(x)

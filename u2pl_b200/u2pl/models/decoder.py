@@ -4,13 +4,14 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from u2pl_b200.fused import run_sequential
+from u2pl_b200.fused import DilatedConv2d, run_sequential
 
 from .base import ASPP, _norm
 
 
 def _head3x3(cin, cout, norm, bias):
-    return [nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1, bias=bias), norm(cout),
+    conv = nn.Conv2d if bias else DilatedConv2d          # bias-free 1280->256 head: GEMM-based weight gradient
+    return [conv(cin, cout, kernel_size=3, stride=1, padding=1, bias=bias), norm(cout),
             nn.ReLU(inplace=True), nn.Dropout2d(0.1)]
 
 
