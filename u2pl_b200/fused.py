@@ -195,3 +195,18 @@ class DilatedConv2d(nn.Conv2d):
         wb = self.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         with torch.autocast("cuda", enabled=False):
             return _DilatedConvFn.apply(xb, wb, d)
+
+
+class StemConv2d(nn.Conv2d):
+    """The 3-channel input convolution (resnet.py:179).  With Cin = 3 cuDNN cannot use its 16-byte aligned
+    bf16 kernels and falls back to wgrad_alg0_engine_NHWC (18 ms per step on B200 for 7 GFLOP).  Padding the
+    input and the weight's Cin with zero channels up to 8 is mathematically the identity and takes the
+    aligned paths; autograd slices the weight gradient back to 3 channels."""
+
+    def forward(self, x):
+        if not (x.is_cuda and self.in_channels < 8 and torch.is_autocast_enabled() and self.groups == 1):
+            return super().forward(x)
+        pad = 8 - self.in_channels
+        x8 = F.pad(x, (0, 0, 0, 0, 0, pad)).contiguous(memory_format=torch.channels_last)
+        w8 = F.pad(self.weight, (0, 0, 0, 0, 0, pad))
+        return F.conv2d(x8, w8, self.bias, self.stride, self.padding, self.dilation, 1)

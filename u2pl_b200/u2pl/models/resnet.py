@@ -4,7 +4,7 @@ sequence, so a state_dict or a torch seed produces the same weights as the refer
 import torch
 import torch.nn as nn
 
-from u2pl_b200.fused import bn_act, run_sequential
+from u2pl_b200.fused import StemConv2d, bn_act, run_sequential
 
 from .base import _norm
 
@@ -84,7 +84,8 @@ class ResNet(nn.Module):
             raise ValueError("replace_stride_with_dilation should be None or a 3-element tuple, "
                              f"got {replace_stride_with_dilation}")
         self.groups, self.base_width, self.fpn = groups, width_per_group, fpn
-        self.conv1 = nn.Sequential(conv3x3(3, 64, stride=2), norm_layer(64), nn.ReLU(inplace=True),
+        stem = StemConv2d(3, 64, kernel_size=3, stride=2, padding=1, bias=False)      # same parameters as conv3x3(3, 64, 2)
+        self.conv1 = nn.Sequential(stem, norm_layer(64), nn.ReLU(inplace=True),
                                    conv3x3(64, 64), norm_layer(64), nn.ReLU(inplace=True),
                                    conv3x3(64, self.inplanes))
         self.bn1 = norm_layer(self.inplanes)
