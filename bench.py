@@ -227,12 +227,12 @@ def our_arm(args):
     lr = cfg["trainer"]["optimizer"]["kwargs"]["lr"]
     params = [dict(params=model.encoder.parameters(), lr=lr), dict(params=model.decoder.parameters(), lr=lr * times)]
     optimizer = get_optimizer(params, cfg["trainer"]["optimizer"])
-    for p in teacher.parameters():
-        p.requires_grad = False
-    if world > 1:
+    if world > 1:                                             # same order as train_semi.py:114-133
         ddp = torch.nn.parallel.DistributedDataParallel
         model = ddp(model, device_ids=[local_rank], output_device=local_rank, find_unused_parameters=False)
         teacher = ddp(teacher, device_ids=[local_rank], output_device=local_rank, find_unused_parameters=False)
+    for p in teacher.parameters():
+        p.requires_grad = False
     sup_loss_fn = get_criterion(cfg)
     memobank, queue_ptrlis, queue_size = [], [], []
     g = torch.Generator().manual_seed(7)
