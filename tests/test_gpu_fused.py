@@ -69,12 +69,12 @@ def test_bn_act_eval_and_fallbacks():
     assert torch.equal(fused.bn_act(x32, bn, nn.ReLU()), F.relu(bn(x32)))
 
 
-@pytest.mark.parametrize("d", [12, 24, 36])
-def test_dilated_conv_weight_grad(d):
+@pytest.mark.parametrize("d,stride", [(12, 1), (24, 1), (36, 1), (1, 1), (1, 2), (2, 2)])
+def test_dilated_conv_weight_grad(d, stride):
     from u2pl_b200 import fused
     torch.manual_seed(d)
-    conv = fused.DilatedConv2d(64, 32, 3, padding=d, dilation=d, bias=False).cuda()
-    ref = nn.Conv2d(64, 32, 3, padding=d, dilation=d, bias=False).cuda()
+    conv = fused.DilatedConv2d(64, 32, 3, stride=stride, padding=d, dilation=d, bias=False).cuda()
+    ref = nn.Conv2d(64, 32, 3, stride=stride, padding=d, dilation=d, bias=False).cuda()
     ref.load_state_dict(conv.state_dict())
     x = torch.randn(2, 64, 33, 31, device="cuda").bfloat16().float()
     xa = _cl(x.clone()).requires_grad_(True)

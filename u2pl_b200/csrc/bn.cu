@@ -198,7 +198,28 @@ bn_bwd_partial_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x,
     for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; mu[j] = mean[cvec * 8 + j]; is[j] = invstd[cvec * 8 + j]; }
     const long long step = static_cast<long long>(gridDim.x) * slots;
     if (slot < slots) {
-        for (long long row = static_cast<long long>(blockIdx.x) * slots + slot; row < M; row += step) {
+        long long row = static_cast<long long>(blockIdx.x) * slots + slot;
+        for (; row + step < M; row += 2 * step) {                      // two rows (6 independent 16 B loads) in flight
+            const long long i0 = row * tpr + cvec, i1 = (row + step) * tpr + cvec;
+            const uint4 a0 = __ldg(dy + i0), b0 = __ldg(x + i0), a1 = __ldg(dy + i1), b1 = __ldg(x + i1);
+            uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+            if (y) { c0 = __ldg(y + i0); c1 = __ldg(y + i1); }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float g[8], xv[8];
+                unpack8(u ? a1 : a0, g);
+                unpack8(u ? b1 : b0, xv);
+                if (y) {
+                    float yv[8];
+                    unpack8(u ? c1 : c0, yv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.0f ? g[j] : 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s1[j] += g[j]; s2[j] = fmaf(g[j], (xv[j] - mu[j]) * is[j], s2[j]); }
+            }
+        }
+        for (; row < M; row += step) {
             const long long i = row * tpr + cvec;
             float g[8], xv[8];
             unpack8(__ldg(dy + i), g);
@@ -276,7 +297,7 @@ static bool bn_shape_ok(long long M, long long C) { return M > 0 && C >= 8 && C 
 
 using namespace u2pl;
 
-constexpr int kBnParts = 148 * 2;
+constexpr int kBnParts = 148 * 4;        // partial-sum blocks: enough 16 B loads in flight to cover HBM latency
 
 extern "C" int64_t u2pl_bn_parts(void) { return kBnParts; }
 

@@ -140,53 +140,62 @@ def run_sequential(seq, x):
 
 # ----------------------------------------------------------------------------- dilated conv
 class _DilatedConvFn(torch.autograd.Function):
+    """3x3 convolution, padding == dilation, stride s: cuDNN forward and data gradient, weight gradient as
+    nine GEMMs over the (cropped, strided) input windows."""
+
     @staticmethod
-    def forward(ctx, x, w, dilation):
+    def forward(ctx, x, w, dilation, stride):
         ctx.save_for_backward(x, w)
-        ctx.dilation = dilation
-        return F.conv2d(x, w, None, 1, dilation, dilation)
+        ctx.cfg = (dilation, stride)
+        return F.conv2d(x, w, None, stride, dilation, dilation)
 
     @staticmethod
     def backward(ctx, gout):
         x, w = ctx.saved_tensors
-        d = ctx.dilation
+        d, s = ctx.cfg
         gout = gout.contiguous(memory_format=torch.channels_last)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.ops.aten.convolution_backward(gout, x, w, None, [1, 1], [d, d], [d, d], False, [0, 0], 1,
+            dx = torch.ops.aten.convolution_backward(gout, x, w, None, [s, s], [d, d], [d, d], False, [0, 0], 1,
                                                      [True, False, False])[0]
         dw = None
         if ctx.needs_input_grad[1]:
             N, Ci, H, W = x.shape
-            Co = w.shape[0]
+            Co, Ho, Wo = w.shape[0], gout.shape[2], gout.shape[3]
             xh = x.permute(0, 2, 3, 1)                   # NHWC views (no copies: both are channels-last)
             gh = gout.permute(0, 2, 3, 1)
             dw = torch.zeros((Co, 3, 3, Ci), dtype=torch.float32, device=x.device)
+
+            def span(k, n_in, n_out):                    # output range whose input index s*o + k*d - d is in range
+                off = k * d - d
+                lo = max(0, -(off // s)) if off < 0 else 0
+                hi = min(n_out - 1, (n_in - 1 - off) // s)
+                return lo, hi, off
+
             for ky in range(3):
-                oy = (ky - 1) * d                        # input row = output row + oy
-                y0, y1 = max(0, -oy), min(H, H - oy)
-                if y1 <= y0:
+                y0, y1, oy = span(ky, H, Ho)
+                if y1 < y0:
                     continue
                 for kx in range(3):
-                    ox = (kx - 1) * d
-                    x0, x1 = max(0, -ox), min(W, W - ox)
-                    if x1 <= x0:
+                    x0, x1, ox = span(kx, W, Wo)
+                    if x1 < x0:
                         continue
-                    g = gh[:, y0:y1, x0:x1, :].reshape(-1, Co)                       # cropped to the overlap:
-                    a = xh[:, y0 + oy:y1 + oy, x0 + ox:x1 + ox, :].reshape(-1, Ci)   # zero padding contributes nothing
+                    g = gh[:, y0:y1 + 1, x0:x1 + 1, :].reshape(-1, Co)              # zero padding contributes nothing:
+                    a = xh[:, s * y0 + oy:s * y1 + oy + 1:s, s * x0 + ox:s * x1 + ox + 1:s, :].reshape(-1, Ci)   # crop to overlap
                     dw[:, ky, kx, :] = torch.mm(g.t(), a).float()
             dw = dw.permute(0, 3, 1, 2).to(w.dtype)
-        return dx, dw, None
+        return dx, dw, None, None
 
 
 class DilatedConv2d(nn.Conv2d):
-    """Same parameters / state_dict as nn.Conv2d; GEMM-based weight gradient for 3x3, stride 1,
-    padding == dilation on CUDA bf16 channels-last inputs.  Used where cuDNN's heuristics fall back to
-    wgrad_alg0_engine (profiled: the three ASPP convs 2048->256 d=12/24/36 and the 1280->256 head conv)."""
+    """Same parameters / state_dict as nn.Conv2d; GEMM-based weight gradient for 3x3 convolutions with
+    padding == dilation (any stride) on CUDA under bf16 autocast.  Used where cuDNN 9's heuristics fall back
+    to wgrad_alg0_engine_NHWC on B200 (profiled: the three ASPP convs 2048->256 d=12/24/36, the 1280->256
+    head conv, the stride-2 3x3 of layer2)."""
 
     def forward(self, x):
-        d = self.dilation[0]
-        fast = (ENABLED["wgrad"] and x.is_cuda and self.kernel_size == (3, 3) and self.stride == (1, 1)
+        d, s = self.dilation[0], self.stride[0]
+        fast = (ENABLED["wgrad"] and x.is_cuda and self.kernel_size == (3, 3) and self.stride == (s, s)
                 and self.padding == (d, d) and self.dilation == (d, d) and self.groups == 1
                 and self.bias is None and torch.is_autocast_enabled() and torch.is_grad_enabled())
         if not fast:
@@ -194,7 +203,7 @@ class DilatedConv2d(nn.Conv2d):
         xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         wb = self.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         with torch.autocast("cuda", enabled=False):
-            return _DilatedConvFn.apply(xb, wb, d)
+            return _DilatedConvFn.apply(xb, wb, d, s)
 
 
 class StemConv2d(nn.Conv2d):

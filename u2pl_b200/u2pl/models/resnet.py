@@ -4,7 +4,7 @@ sequence, so a state_dict or a torch seed produces the same weights as the refer
 import torch
 import torch.nn as nn
 
-from u2pl_b200.fused import StemConv2d, bn_act, run_sequential
+from u2pl_b200.fused import DilatedConv2d, StemConv2d, bn_act, run_sequential
 
 from .base import _norm
 
@@ -14,8 +14,9 @@ model_urls = {name: f"/path/to/{name}.pth" for name in ("resnet18", "resnet34", 
 
 
 def conv3x3(cin, cout, stride=1, groups=1, dilation=1):
-    return nn.Conv2d(cin, cout, kernel_size=3, stride=stride, padding=dilation, groups=groups, bias=False,
-                     dilation=dilation)
+    conv = DilatedConv2d if stride != 1 else nn.Conv2d       # strided 3x3: GEMM-based weight gradient (fused.py)
+    return conv(cin, cout, kernel_size=3, stride=stride, padding=dilation, groups=groups, bias=False,
+                dilation=dilation)
 
 
 def conv1x1(cin, cout, stride=1):
@@ -84,7 +85,7 @@ class ResNet(nn.Module):
             raise ValueError("replace_stride_with_dilation should be None or a 3-element tuple, "
                              f"got {replace_stride_with_dilation}")
         self.groups, self.base_width, self.fpn = groups, width_per_group, fpn
-        stem = StemConv2d(3, 64, kernel_size=3, stride=2, padding=1, bias=False)      # same parameters as conv3x3(3, 64, 2)
+        stem = StemConv2d(3, 64, kernel_size=3, stride=2, padding=1, bias=False, dilation=1)   # = conv3x3(3, 64, 2)
         self.conv1 = nn.Sequential(stem, norm_layer(64), nn.ReLU(inplace=True),
                                    conv3x3(64, 64), norm_layer(64), nn.ReLU(inplace=True),
                                    conv3x3(64, self.inplanes))
