@@ -14,7 +14,9 @@ model_urls = {name: f"/path/to/{name}.pth" for name in ("resnet18", "resnet34", 
 
 
 def conv3x3(cin, cout, stride=1, groups=1, dilation=1):
-    conv = DilatedConv2d if stride != 1 else nn.Conv2d       # strided 3x3: GEMM-based weight gradient (fused.py)
+    # strided or strongly dilated 3x3 (layer2.0, layer4 d=4/8/16): GEMM-based weight gradient (fused.py);
+    # cuDNN 9 falls back to wgrad_alg0_engine for some of them on B200 (18 ms for one 512->512 d=16 layer)
+    conv = DilatedConv2d if (stride != 1 or dilation >= 4) else nn.Conv2d
     return conv(cin, cout, kernel_size=3, stride=stride, padding=dilation, groups=groups, bias=False,
                 dilation=dilation)
 
