@@ -58,6 +58,20 @@ int u2pl_entropy_thresholds(const float *logits, const int64_t *target,
                             float *entropy, float *thresh, int64_t *n_valid,
                             void *ws, size_t ws_bytes, void *stream);
 
+/* Two-level variant ("exact where it matters"): same thresholds (bit-identical) and therefore the same
+ * masks as u2pl_entropy_thresholds, but the entropy map is evaluated with hardware ex2/lg2
+ * (|error| <= 1e-4 against the contract arithmetic) and re-evaluated under the contract only for pixels
+ * within 3e-4 of a target order statistic's 22-bit key bin; those exact values are stored back, so
+ * every later `entropy <=/>= thresh[j]` comparison on the returned map is exact.  The heavy pass is
+ * HBM-bound instead of issue-bound.  C in {19, 21}; other C fall through to the exact-everywhere path.
+ * Workspace: u2pl_entropy_fast_ws_bytes (holds the per-target candidate lists). */
+size_t u2pl_entropy_fast_ws_bytes(int64_t B, int64_t HW);
+int u2pl_entropy_thresholds_fast(const float *logits, const int64_t *target,
+                                 int64_t B, int64_t C, int64_t HW, int64_t ignore,
+                                 const float *h_percents, int nq,
+                                 float *entropy, float *thresh, int64_t *n_valid,
+                                 void *ws, size_t ws_bytes, void *stream);
+
 /* ------------------------------------------------------------------------
  * A6  reliable/unreliable partition of the pseudo-label target
  * replaces: loss_helper.py:41-44

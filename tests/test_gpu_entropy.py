@@ -23,6 +23,20 @@ def _dev(a, dtype=None):
     return t.cuda()
 
 
+def _check_entropy_map(e, e_or, th, valid, exact_map):
+    """exact_map: every value bit-equal to the oracle.  Two-level path: values within 2.5e-5 of the contract
+    (quarter of the kernel's guard kDelta = 1e-4), bit-equal inside the guard band of every threshold, and every
+    comparison against every threshold identical to the oracle's."""
+    if exact_map:
+        assert np.array_equal(e.view(np.uint32), e_or.view(np.uint32))
+        return
+    assert np.abs(e - e_or).max() <= 2.5e-5
+    for t in th[np.isfinite(th)]:
+        near = np.abs(e_or - t) <= 1e-4
+        assert np.array_equal(e[near & valid].view(np.uint32), e_or[near & valid].view(np.uint32))
+        assert np.array_equal((e >= t) & valid, (e_or >= t) & valid) and np.array_equal((e <= t) & valid, (e_or <= t) & valid)
+
+
 def _rand_case(rng, B, C, H, W, frac_ignore=0.0, scale=3.0):
     h, w = max(2, H // 4), max(2, W // 4)
     x = torch.from_numpy(rng.standard_normal((B, C, h, w)).astype(np.float32)) * scale
@@ -60,13 +74,14 @@ def test_unsup_loss_golden(golden, name):
     (1, 21, 5, 3, 0.0, [20.0, 80.0]),                     # tiny, ragged
     (2, 21, 64, 64, 0.95, [95.0]),                        # almost everything ignored
 ])
-def test_entropy_thresholds_bit_exact(B, C, H, W, ign, percents):
+@pytest.mark.parametrize("exact_map", [True, False])
+def test_entropy_thresholds_bit_exact(B, C, H, W, ign, percents, exact_map):
     ops = _ops()
     rng = np.random.default_rng(B * 1000 + C * 10 + H)
     x, target = _rand_case(rng, B, C, H, W, ign)
-    ent, thresh, n_valid = ops.entropy_thresholds(_dev(x), _dev(target), percents)
+    ent, thresh, n_valid = ops.entropy_thresholds(_dev(x), _dev(target), percents, exact_map=exact_map)
     ent_or = port.entropy(x)
-    assert np.array_equal(ent.cpu().numpy().view(np.uint32), ent_or.view(np.uint32))
+    _check_entropy_map(ent.cpu().numpy(), ent_or, thresh.cpu().numpy(), target != 255, exact_map)
     valid = target != 255
     assert n_valid.item() == int(valid.sum())
     th = thresh.cpu().numpy()
@@ -81,9 +96,10 @@ def test_all_ignored_gives_nan():
     rng = np.random.default_rng(0)
     x, target = _rand_case(rng, 1, 21, 16, 16)
     target[:] = 255
-    ent, thresh, n_valid = ops.entropy_thresholds(_dev(x), _dev(target), [80.0])
-    assert n_valid.item() == 0 and np.isnan(thresh.cpu().numpy()[0])
-    assert np.array_equal(ent.cpu().numpy(), port.entropy(x))
+    for exact_map in (True, False):
+        ent, thresh, n_valid = ops.entropy_thresholds(_dev(x), _dev(target), [80.0], exact_map=exact_map)
+        assert n_valid.item() == 0 and np.isnan(thresh.cpu().numpy()[0])
+        assert np.abs(ent.cpu().numpy() - port.entropy(x)).max() <= (0 if exact_map else 2.5e-5)
 
 
 def test_heavy_ties_and_constant_logits():
@@ -91,9 +107,9 @@ def test_heavy_ties_and_constant_logits():
     x = np.zeros((2, 21, 24, 24), np.float32)                       # every pixel has the same entropy
     x[1, 3] = 5.0
     target = np.zeros((2, 24, 24), np.int64)
-    ent, thresh, _ = ops.entropy_thresholds(_dev(x), _dev(target), [50.0, 99.0])
+    ent, thresh, _ = ops.entropy_thresholds(_dev(x), _dev(target), [50.0, 99.0])       # two-level path, all pixels tie
     ent_or = port.entropy(x)
-    assert np.array_equal(ent.cpu().numpy(), ent_or)
+    assert np.array_equal(ent.cpu().numpy(), ent_or)                                   # everything is a candidate -> exact
     assert thresh.cpu().numpy()[0] == port.percentile(ent_or, 50.0)
     assert thresh.cpu().numpy()[1] == port.percentile(ent_or, 99.0)
     t = _dev(target)
@@ -148,7 +164,12 @@ def test_full_size_v16_properties():
     x = torch.nn.functional.interpolate(low, (H, W), mode="bilinear", align_corners=True).contiguous()
     target = x.argmax(1)
     percents = [90.0, 10.0, 90.0000001, 100.0]
-    ent, thresh, n_valid = ops.entropy_thresholds(x, target, percents)
+    ent, thresh, n_valid = ops.entropy_thresholds(x, target, percents, exact_map=True)
+    ent_f, thresh_f, _ = ops.entropy_thresholds(x, target, percents)                   # two-level path
+    assert torch.equal(thresh, thresh_f)                                               # bit-identical thresholds
+    for j in range(len(percents)):
+        assert torch.equal(ent >= thresh[j], ent_f >= thresh[j]) and torch.equal(ent <= thresh[j], ent_f <= thresh[j])
+    assert (ent - ent_f).abs().max().item() <= 2.5e-5
     e = ent.cpu().numpy().ravel()
     th = thresh.cpu().numpy()
     for j, q in enumerate(percents):

@@ -28,6 +28,7 @@ def main():
     target = x.argmax(1)
     N = B * H * W
     res = {}
+    res["entropy_thresholds_exact_1q_us"] = timeit(lambda: ops.entropy_thresholds(x, target, [90.0], exact_map=True))
     res["entropy_thresholds_1q_us"] = timeit(lambda: ops.entropy_thresholds(x, target, [90.0]))
     res["entropy_thresholds_3q_us"] = timeit(lambda: ops.entropy_thresholds(x, target, [90.0, 10.0, 90.0]))
     ent, th, _ = ops.entropy_thresholds(x, target, [90.0])

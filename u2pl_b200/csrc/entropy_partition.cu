@@ -27,10 +27,14 @@ constexpr uint32_t kInvalidKey = 0xFFFFFFFFu;
 
 struct SelState {
     uint32_t prefix[kMaxT];
-    uint32_t rank[kMaxT];
+    uint32_t rank[kMaxT];           // rank inside the current prefix bin
     float    gamma[kMaxQ];
     uint32_t n;
-    uint32_t pad[3];
+    uint32_t done;                  // two-level path: blocks of exact_select that have finished
+    uint32_t grank[kMaxT];          // global rank of every target order statistic
+    uint32_t cnt[kMaxT];            // two-level path: candidates gathered per target
+    uint32_t below[kMaxT];          //                 valid pixels surely below the candidate band
+    float    val[kMaxT];            //                 exact order statistics
 };
 
 struct Percents { float q[kMaxQ]; int use_rank; uint32_t rank; };   // use_rank: one explicit order statistic instead
@@ -171,7 +175,7 @@ select1_kernel(const uint32_t *__restrict__ hist1, SelState *__restrict__ st, Pe
             uint32_t cum = excl;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                if (r < cum + loc[j]) { st->prefix[t] = tid * 16 + j; st->rank[t] = r - cum; break; }
+                if (r < cum + loc[j]) { st->prefix[t] = tid * 16 + j; st->rank[t] = r - cum; st->grank[t] = r; break; }
                 cum += loc[j];
             }
         }
@@ -337,6 +341,206 @@ entropy_masks_kernel(const float *__restrict__ ent, const int64_t *__restrict__ 
     }
 }
 
+
+
+// ====================================================================== two-level path
+// "Exact where it matters".  The masks only depend on how every entropy compares with the
+// thresholds, and the thresholds only depend on a few order statistics.  So:
+//   F1 entropy_fast_hist   entropies with hardware ex2/lg2 (2 MUFU + ~6 FP32 ops per class instead of
+//                          ~43 issue slots): HBM-bound.  |fast - contract| <= kDelta (see below).
+//   F2 select1 + hist_refine<2> + select_refine on the FAST keys: a 22-bit key bin per target rank
+//   F3 candidates          every valid pixel whose fast entropy lies within 3*kDelta of a target's bin is
+//                          re-evaluated under the arithmetic contract (exact value stored back into
+//                          `entropy`, exact key appended to the target's candidate list); pixels surely
+//                          below the band are only counted
+//   F4 exact_select        per target: radix select of rank (global rank - #below) among its candidates;
+//                          last block: numpy lerp -> thresholds
+// Soundness: order statistics are 1-Lipschitz in the sup norm, so the exact r-th value is within kDelta
+// of the fast r-th value, which lies in the target's bin.  Non-candidates below (above) the band have
+// exact values < bin.lo - 2*kDelta (> bin.hi + 2*kDelta): their order relative to the exact statistic
+// is known, hence rank_in_candidates = r - #below.  Every later comparison `entropy <=/>= threshold`
+// is exact for candidates (exact values stored) and decided by a margin > kDelta for all others.
+// If the invariant 0 <= rank_in_candidates < #candidates is ever violated the thresholds are set to NaN.
+constexpr float kDelta = 1.0e-4f;     // bound on |fast - contract| (measured max ~3e-6; tests assert < kDelta/4)
+
+template <int C>
+__device__ __forceinline__ float entropy_fast_of(float (&v)[C])
+{
+    float m = v[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmaxf(m, v[c]);
+    const float ml = m * 1.4426950408889634f;
+    float S = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { v[c] = exp2f(fmaf(v[c], 1.4426950408889634f, -ml)); S += v[c]; }
+    const float rinv = __fdividef(1.0f, S);
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float p = v[c] * rinv;
+        acc = fmaf(p, __log2f(p + 1e-10f), acc);
+    }
+    return -0.6931471805599453f * acc;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kEntThreads)
+entropy_fast_hist_kernel(const float *__restrict__ logits, const int64_t *__restrict__ target,
+                         uint32_t HW, uint32_t N, int64_t ignore,
+                         float *__restrict__ ent, uint32_t *__restrict__ keys, uint32_t *__restrict__ hist1)
+{
+    __shared__ uint32_t sh[kBins1];
+    for (int j = threadIdx.x; j < kBins1; j += kEntThreads) sh[j] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * kEntThreads + threadIdx.x; i < N; i += gridDim.x * kEntThreads) {
+        const uint32_t b = i / HW, p = i - b * HW;
+        const float *x = logits + static_cast<size_t>(b) * C * HW + p;
+        float v[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
+        const int64_t t = __ldg(target + i);
+        const float h = entropy_fast_of<C>(v);
+        ent[i] = h;
+        const bool valid = (t != ignore);
+        const uint32_t key = valid ? float_key(h) : kInvalidKey;
+        keys[i] = key;
+        if (valid) hist_add(sh, key >> 20);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < kBins1; j += kEntThreads)
+        if (sh[j]) atomicAdd(&hist1[j], sh[j]);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+candidate_kernel(const float *__restrict__ logits, const uint32_t *__restrict__ keys, uint32_t HW, uint32_t N,
+                 SelState *__restrict__ st, int T, float *__restrict__ ent, uint32_t *__restrict__ lists)
+{
+    if (st->n == 0) return;
+    float lo[kMaxT], hi[kMaxT];
+    uint32_t below[kMaxT];
+#pragma unroll
+    for (int t = 0; t < kMaxT; ++t) {
+        below[t] = 0;
+        if (t < T) {
+            const uint32_t pre = st->prefix[t];                       // 22-bit bin of the fast keys
+            lo[t] = key_float(pre << 10) - 3.0f * kDelta;
+            hi[t] = (pre == 0x3FFFFFu) ? __uint_as_float(0x7f800000u) : key_float((pre + 1u) << 10) + 3.0f * kDelta;
+        } else { lo[t] = __uint_as_float(0x7f800000u); hi[t] = lo[t]; }
+    }
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < N; i += gridDim.x * 256u) {
+        const uint32_t k = __ldg(keys + i);
+        if (k == kInvalidKey) continue;
+        const float h = key_float(k);
+        uint32_t hit = 0;
+#pragma unroll
+        for (int t = 0; t < kMaxT; ++t) {
+            if (t < T) {
+                if (h < lo[t]) ++below[t];
+                else if (h < hi[t]) hit |= (1u << t);
+            }
+        }
+        if (hit) {                                                    // rare: re-evaluate under the contract
+            const uint32_t b = i / HW, p = i - b * HW;
+            const float *x = logits + static_cast<size_t>(b) * C * HW + p;
+            float v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
+            const float e = entropy_of<C>(v);
+            ent[i] = e;
+            const uint32_t ek = float_key(e);
+            while (hit) {
+                const int t = __ffs(hit) - 1;
+                hit &= hit - 1;
+                const uint32_t pos = atomicAdd(&st->cnt[t], 1u);
+                lists[static_cast<size_t>(t) * N + pos] = ek;
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kMaxT; ++t) {
+        if (t < T) {
+            const uint32_t s = static_cast<uint32_t>(warp_sum_i(static_cast<int>(below[t])));
+            if ((threadIdx.x & 31) == 0 && s) atomicAdd(&st->below[t], s);
+        }
+    }
+}
+
+// one block per target: 11/11/10-bit radix select inside the candidate list; the last block to finish
+// turns the exact order statistics into thresholds (numpy's two-sided lerp).
+__global__ void __launch_bounds__(1024)
+exact_select_kernel(const uint32_t *__restrict__ lists, uint32_t N, SelState *__restrict__ st, int nq,
+                    float *__restrict__ thresh, int64_t *__restrict__ n_valid)
+{
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_prefix, s_rank;
+    __shared__ int s_last;
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t n_all = st->n;
+    if (n_all != 0) {
+        const uint32_t n = st->cnt[t];
+        const uint32_t r0 = st->grank[t] - st->below[t];              // unsigned: a violated invariant shows as r0 >= n
+        const uint32_t *list = lists + static_cast<size_t>(t) * N;
+        if (r0 >= n) {
+            if (tid == 0) st->val[t] = __uint_as_float(0x7fc00000u);
+        } else {
+            if (tid == 0) { s_prefix = 0; s_rank = r0; }
+            const int shifts[3] = {21, 10, 0}, nbits[3] = {11, 11, 10};
+            for (int pass = 0; pass < 3; ++pass) {
+                hist[tid] = 0; hist[tid + 1024] = 0;
+                __syncthreads();
+                const uint32_t pre = s_prefix, r = s_rank;
+                const int sh = shifts[pass], hb = sh + nbits[pass];
+                const uint32_t mask = (1u << nbits[pass]) - 1u;
+                for (uint32_t j = tid; j < n; j += 1024) {
+                    const uint32_t k = __ldg(list + j);
+                    if (pass == 0 || (k >> hb) == pre) atomicAdd(&hist[(k >> sh) & mask], 1u);
+                }
+                __syncthreads();
+                const uint32_t c0 = hist[2 * tid], c1 = hist[2 * tid + 1], sum = c0 + c1;
+                uint32_t inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += y;
+                }
+                if (lane == 31) warp_tot[wid] = inc;
+                __syncthreads();
+                uint32_t base = 0;
+                for (int w = 0; w < wid; ++w) base += warp_tot[w];
+                const uint32_t excl = base + inc - sum;
+                __syncthreads();
+                if (r >= excl && r < excl + sum) {
+                    const uint32_t bin = (r < excl + c0) ? 2 * tid : 2 * tid + 1;
+                    s_prefix = (pre << nbits[pass]) | bin;
+                    s_rank = r - ((r < excl + c0) ? excl : excl + c0);
+                }
+                __syncthreads();
+            }
+            if (tid == 0) st->val[t] = key_float(s_prefix);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&st->done, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        for (int j = 0; j < nq; ++j) {
+            if (n_all == 0) { thresh[j] = __uint_as_float(0x7fc00000u); continue; }
+            const volatile float *vv = st->val;
+            const float a = vv[2 * j], b = vv[2 * j + 1], g = st->gamma[j];
+            const float d = __fadd_rn(b, -a);
+            float r = __fadd_rn(a, __fmul_rn(d, g));
+            if (g >= 0.5f) r = __fadd_rn(b, -__fmul_rn(d, __fadd_rn(1.0f, -g)));
+            thresh[j] = r;
+        }
+        if (n_valid) *n_valid = static_cast<int64_t>(n_all);
+    }
+}
 
 // ------------------------------------------------------------------ OHEM (loss_helper.py:502-531)
 // mask_prob = softmax(pred)[target] (1.0 where target == ignore), computed under the arithmetic
@@ -535,6 +739,62 @@ extern "C" int u2pl_entropy_thresholds(const float *logits, const int64_t *targe
     hist_refine_kernel<3><<<g2, 256, smem, s>>>(w.keys, N, w.st, w.hist3, T);
     select_refine_kernel<true><<<1, 1024, 0, s>>>(w.hist3, w.st, nq, thresh, n_valid);
     return check_launch("entropy_thresholds select chain", 5);
+}
+
+
+static size_t fast_ws_layout(int64_t N, void *base, EntropyWs *out, uint32_t **lists)
+{
+    const size_t head = ws_layout(N, base, out);
+    if (lists) *lists = reinterpret_cast<uint32_t *>(static_cast<char *>(base) + head);
+    return head + align256(static_cast<size_t>(kMaxT) * static_cast<size_t>(N) * 4);
+}
+
+extern "C" size_t u2pl_entropy_fast_ws_bytes(int64_t B, int64_t HW) { return fast_ws_layout(B * HW, nullptr, nullptr, nullptr); }
+
+extern "C" int u2pl_entropy_thresholds_fast(const float *logits, const int64_t *target,
+                                            int64_t B, int64_t C, int64_t HW, int64_t ignore,
+                                            const float *h_percents, int nq,
+                                            float *entropy, float *thresh, int64_t *n_valid,
+                                            void *ws, size_t ws_bytes, void *stream)
+{
+    if (C != 19 && C != 21)      // the two-level path is specialised for the class counts of the shipped configs
+        return u2pl_entropy_thresholds(logits, target, B, C, HW, ignore, h_percents, nq, entropy, thresh, n_valid, ws, ws_bytes, stream);
+    if (B <= 0 || HW <= 0) return bad_arg("entropy_thresholds_fast: empty shape");
+    if (nq < 1 || nq > kMaxQ) return bad_arg("entropy_thresholds_fast: nq must be in [1, U2PL_MAX_QUANTILES]");
+    if (B * HW >= (1LL << 31)) return bad_arg("entropy_thresholds_fast: B*HW must be < 2^31");
+    if (ws_bytes < fast_ws_layout(B * HW, nullptr, nullptr, nullptr)) { set_error("entropy_thresholds_fast: workspace too small"); return U2PL_E_WS_SMALL; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t N = static_cast<uint32_t>(B * HW), hw = static_cast<uint32_t>(HW);
+    EntropyWs w;
+    uint32_t *lists = nullptr;
+    fast_ws_layout(B * HW, ws, &w, &lists);
+    cudaError_t e = cudaMemsetAsync(w.hist1, 0, w.zero_bytes, s);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
+    Percents pc;
+    pc.use_rank = 0; pc.rank = 0;
+    for (int j = 0; j < kMaxQ; ++j) pc.q[j] = (j < nq) ? h_percents[j] : 0.0f;
+    const int T = 2 * nq;
+    if (C == 19) {
+        const int g = grid_for(reinterpret_cast<const void *>(entropy_fast_hist_kernel<19>), kEntThreads, 0, N);
+        entropy_fast_hist_kernel<19><<<g, kEntThreads, 0, s>>>(logits, target, hw, N, ignore, entropy, w.keys, w.hist1);
+    } else {
+        const int g = grid_for(reinterpret_cast<const void *>(entropy_fast_hist_kernel<21>), kEntThreads, 0, N);
+        entropy_fast_hist_kernel<21><<<g, kEntThreads, 0, s>>>(logits, target, hw, N, ignore, entropy, w.keys, w.hist1);
+    }
+    select1_kernel<<<1, 256, 0, s>>>(w.hist1, w.st, pc, nq);
+    const size_t smem = static_cast<size_t>(T) * kBinsR * 4;
+    const int g2 = grid_for(reinterpret_cast<const void *>(hist_refine_kernel<2>), 256, smem, N, 4);
+    hist_refine_kernel<2><<<g2, 256, smem, s>>>(w.keys, N, w.st, w.hist2, T);
+    select_refine_kernel<false><<<1, 1024, 0, s>>>(w.hist2, w.st, nq, thresh, nullptr);
+    if (C == 19) {
+        const int g = grid_for(reinterpret_cast<const void *>(candidate_kernel<19>), 256, 0, N);
+        candidate_kernel<19><<<g, 256, 0, s>>>(logits, w.keys, hw, N, w.st, T, entropy, lists);
+    } else {
+        const int g = grid_for(reinterpret_cast<const void *>(candidate_kernel<21>), 256, 0, N);
+        candidate_kernel<21><<<g, 256, 0, s>>>(logits, w.keys, hw, N, w.st, T, entropy, lists);
+    }
+    exact_select_kernel<<<T, 1024, 0, s>>>(lists, N, w.st, nq, thresh, n_valid);
+    return check_launch("entropy_thresholds_fast", 6);
 }
 
 extern "C" int u2pl_partition_target(const float *entropy, int64_t *target, int64_t n, int64_t ignore,

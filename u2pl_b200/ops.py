@@ -43,11 +43,14 @@ def _f32c(t):
 
 
 # --------------------------------------------------------------------------- entropy / percentiles
-def entropy_thresholds(logits, target, percents, ignore=255):
+def entropy_thresholds(logits, target, percents, ignore=255, exact_map=False):
     """Softmax entropy of `logits` [B,C,H,W] + np.percentile-compatible thresholds.
 
     Mirrors loss_helper.py:35-40 / train_semi.py:402-415.  Returns (entropy [B,H,W] fp32,
-    thresh [len(percents)] fp32 device tensor, n_valid int64 device scalar)."""
+    thresh [len(percents)] fp32 device tensor, n_valid int64 device scalar).
+    exact_map=False (default): two-level path -- thresholds and every comparison against them are exact,
+    the entropy map itself is exact only near the thresholds (elsewhere within 1e-4 of the contract).
+    exact_map=True: contract arithmetic for every pixel."""
     _need_cuda(logits, target)
     lib = _lib.load()
     logits = _f32c(logits)
@@ -59,12 +62,16 @@ def entropy_thresholds(logits, target, percents, ignore=255):
     ent = torch.empty((B, H, W), dtype=torch.float32, device=logits.device)
     thresh = torch.empty(nq, dtype=torch.float32, device=logits.device)
     n_valid = torch.empty((), dtype=torch.int64, device=logits.device)
-    nbytes = lib.u2pl_entropy_ws_bytes(B, HW)
-    ws = _workspace("entropy", nbytes, logits.device)
     hq = (ctypes.c_float * nq)(*[float(q) for q in percents])
-    rc = lib.u2pl_entropy_thresholds(_p(logits), _p(target), B, C, HW, int(ignore), hq, nq,
-                                     _p(ent), _p(thresh), _p(n_valid), _p(ws), ws.numel(), _stream())
-    _lib.check(rc, "u2pl_entropy_thresholds")
+    if exact_map:
+        ws = _workspace("entropy", lib.u2pl_entropy_ws_bytes(B, HW), logits.device)
+        fn, name = lib.u2pl_entropy_thresholds, "u2pl_entropy_thresholds"
+    else:
+        ws = _workspace("entropy_fast", lib.u2pl_entropy_fast_ws_bytes(B, HW), logits.device)
+        fn, name = lib.u2pl_entropy_thresholds_fast, "u2pl_entropy_thresholds_fast"
+    rc = fn(_p(logits), _p(target), B, C, HW, int(ignore), hq, nq,
+            _p(ent), _p(thresh), _p(n_valid), _p(ws), ws.numel(), _stream())
+    _lib.check(rc, name)
     return ent, thresh, n_valid
 
 
