@@ -348,8 +348,8 @@ entropy_masks_kernel(const float *__restrict__ ent, const int64_t *__restrict__ 
 // thresholds, and the thresholds only depend on a few order statistics.  So:
 //   F1 entropy_fast_hist   entropies with hardware ex2/lg2 (2 MUFU + ~6 FP32 ops per class instead of
 //                          ~43 issue slots): HBM-bound.  |fast - contract| <= kDelta (see below).
-//   F2 select1 + hist_refine<2> + select_refine on the FAST keys: a 22-bit key bin per target rank
-//   F3 candidates          every valid pixel whose fast entropy lies within 3*kDelta of a target's bin is
+//   F2 fast_refine         select1 + 10-bit histogram on the FAST keys: a 22-bit key bin per target rank
+//   F3 fast_candidate      every valid pixel whose fast entropy lies within 3*kDelta of a target's bin is
 //                          re-evaluated under the arithmetic contract (exact value stored back into
 //                          `entropy`, exact key appended to the target's candidate list); pixels surely
 //                          below the band are only counted
@@ -409,61 +409,6 @@ entropy_fast_hist_kernel(const float *__restrict__ logits, const int64_t *__rest
     __syncthreads();
     for (int j = threadIdx.x; j < kBins1; j += kEntThreads)
         if (sh[j]) atomicAdd(&hist1[j], sh[j]);
-}
-
-template <int C>
-__global__ void __launch_bounds__(256)
-candidate_kernel(const float *__restrict__ logits, const uint32_t *__restrict__ keys, uint32_t HW, uint32_t N,
-                 SelState *__restrict__ st, int T, float *__restrict__ ent, uint32_t *__restrict__ lists)
-{
-    if (st->n == 0) return;
-    float lo[kMaxT], hi[kMaxT];
-    uint32_t below[kMaxT];
-#pragma unroll
-    for (int t = 0; t < kMaxT; ++t) {
-        below[t] = 0;
-        if (t < T) {
-            const uint32_t pre = st->prefix[t];                       // 22-bit bin of the fast keys
-            lo[t] = key_float(pre << 10) - 3.0f * kDelta;
-            hi[t] = (pre == 0x3FFFFFu) ? __uint_as_float(0x7f800000u) : key_float((pre + 1u) << 10) + 3.0f * kDelta;
-        } else { lo[t] = __uint_as_float(0x7f800000u); hi[t] = lo[t]; }
-    }
-    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < N; i += gridDim.x * 256u) {
-        const uint32_t k = __ldg(keys + i);
-        if (k == kInvalidKey) continue;
-        const float h = key_float(k);
-        uint32_t hit = 0;
-#pragma unroll
-        for (int t = 0; t < kMaxT; ++t) {
-            if (t < T) {
-                if (h < lo[t]) ++below[t];
-                else if (h < hi[t]) hit |= (1u << t);
-            }
-        }
-        if (hit) {                                                    // rare: re-evaluate under the contract
-            const uint32_t b = i / HW, p = i - b * HW;
-            const float *x = logits + static_cast<size_t>(b) * C * HW + p;
-            float v[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
-            const float e = entropy_of<C>(v);
-            ent[i] = e;
-            const uint32_t ek = float_key(e);
-            while (hit) {
-                const int t = __ffs(hit) - 1;
-                hit &= hit - 1;
-                const uint32_t pos = atomicAdd(&st->cnt[t], 1u);
-                lists[static_cast<size_t>(t) * N + pos] = ek;
-            }
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < kMaxT; ++t) {
-        if (t < T) {
-            const uint32_t s = static_cast<uint32_t>(warp_sum_i(static_cast<int>(below[t])));
-            if ((threadIdx.x & 31) == 0 && s) atomicAdd(&st->below[t], s);
-        }
-    }
 }
 
 // one block per target: 11/11/10-bit radix select inside the candidate list; the last block to finish
@@ -539,6 +484,232 @@ exact_select_kernel(const uint32_t *__restrict__ lists, uint32_t N, SelState *__
             thresh[j] = r;
         }
         if (n_valid) *n_valid = static_cast<int64_t>(n_all);
+    }
+}
+
+
+// ---- fused launches of the two-level path -------------------------------------------------------------
+// The tiny single-block select kernels are folded into the prologue of the pass that consumes them (every
+// block repeats the ~16 KB histogram scan; block 0 publishes the result), so the chain is
+//   entropy_fast_hist -> fast_refine (select1 + 10-bit histogram) -> fast_candidate (select + band test +
+//   exact re-evaluation) -> exact_select (+ lerp).
+
+// select1 for all targets, executed by one 256-thread block; results in shared arrays.
+__device__ __forceinline__ void block_select1(const uint32_t *__restrict__ hist1, const Percents &pc, int nq,
+                                              uint32_t *s_prefix, uint32_t *s_rank, uint32_t *s_grank, float *s_gamma,
+                                              uint32_t *s_n, uint32_t *warp_tot)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t loc[16], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { loc[j] = __ldg(hist1 + tid * 16 + j); sum += loc[j]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < wid; ++w) base += warp_tot[w];
+    const uint32_t excl = base + inc - sum;
+    if (tid == 255) *s_n = excl + sum;
+    __syncthreads();
+    const uint32_t n = *s_n;
+    if (tid == 0) {
+        const float nm1 = __uint2float_rn(n ? n - 1u : 0u);
+        for (int j = 0; j < nq; ++j) {                    // numpy 2.x float32 virtual index (see select1_kernel)
+            const float q32 = __fdiv_rn(pc.q[j], 100.0f);
+            const float v = __fmul_rn(nm1, q32);
+            const float fl = floorf(v);
+            uint32_t lo, hi;
+            if (n == 0) { lo = hi = 0; }
+            else if (v >= nm1) { lo = hi = n - 1u; }
+            else { lo = static_cast<uint32_t>(fl); hi = lo + 1u; }
+            s_gamma[j] = __fadd_rn(v, -fl);
+            s_grank[2 * j] = lo;
+            s_grank[2 * j + 1] = hi;
+        }
+    }
+    __syncthreads();
+    if (n == 0) return;
+    for (int t = 0; t < 2 * nq; ++t) {
+        const uint32_t r = s_grank[t];
+        if (r >= excl && r < excl + sum) {
+            uint32_t cum = excl;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (r < cum + loc[j]) { s_prefix[t] = tid * 16 + j; s_rank[t] = r - cum; break; }
+                cum += loc[j];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+fast_refine_kernel(const uint32_t *__restrict__ keys, uint32_t N, const uint32_t *__restrict__ hist1,
+                   SelState *__restrict__ st, Percents pc, int nq, uint32_t *__restrict__ hist2)
+{
+    extern __shared__ uint32_t sh[];                      // [T][1024]
+    __shared__ uint32_t s_prefix[kMaxT], s_rank[kMaxT], s_grank[kMaxT], s_n, warp_tot[8];
+    __shared__ float s_gamma[kMaxQ];
+    const int T = 2 * nq;
+    for (int j = threadIdx.x; j < T * kBinsR; j += 256) sh[j] = 0;
+    block_select1(hist1, pc, nq, s_prefix, s_rank, s_grank, s_gamma, &s_n, warp_tot);
+    const uint32_t n = s_n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->n = n;
+        for (int t = 0; t < T; ++t) { st->prefix[t] = s_prefix[t]; st->rank[t] = s_rank[t]; st->grank[t] = s_grank[t]; }
+        for (int j = 0; j < nq; ++j) st->gamma[j] = s_gamma[j];
+    }
+    if (n == 0) return;
+    uint32_t pre[kMaxT];
+    uint32_t own_mask = 0;                                // targets that own a histogram (first of equal prefixes)
+#pragma unroll
+    for (int t = 0; t < kMaxT; ++t) {
+        pre[t] = (t < T) ? s_prefix[t] : kInvalidKey;
+        bool dup = false;
+#pragma unroll
+        for (int u = 0; u < t; ++u) dup = dup || (t < T && pre[u] == pre[t]);
+        if (t < T && !dup) own_mask |= (1u << t);
+    }
+    __syncthreads();
+    const uint32_t n4 = N >> 2;
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n4 + 1; i += gridDim.x * 256u) {
+        uint32_t kk[4];
+        if (i < n4) { const uint4 q = __ldg(k4 + i); kk[0] = q.x; kk[1] = q.y; kk[2] = q.z; kk[3] = q.w; }
+        else { for (int e = 0; e < 4; ++e) kk[e] = ((n4 << 2) + e < N) ? keys[(n4 << 2) + e] : kInvalidKey; }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t key = kk[e];
+            if (key == kInvalidKey) continue;
+            const uint32_t hi = key >> 20;
+            uint32_t mt = 0;
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) mt |= (((own_mask >> t) & 1u) && hi == pre[t]) ? (1u << t) : 0u;
+            if (mt) {
+                const uint32_t bin = (key >> 10) & (kBinsR - 1);
+                const uint32_t peers = __match_any_sync(__activemask(), (mt << 10) | bin);
+                if ((threadIdx.x & 31) == __ffs(peers) - 1) {
+                    const uint32_t cnt = __popc(peers);
+                    while (mt) { const int t = __ffs(mt) - 1; mt &= mt - 1; atomicAdd(&sh[t * kBinsR + bin], cnt); }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < T * kBinsR; j += 256)
+        if (sh[j]) atomicAdd(&hist2[j], sh[j]);
+}
+
+constexpr int kCandTile = 4096;                            // pixels scanned per block iteration
+
+template <int C>
+__global__ void __launch_bounds__(256)
+fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restrict__ keys, uint32_t HW, uint32_t N,
+                      const uint32_t *__restrict__ hist2, SelState *__restrict__ st, int T,
+                      float *__restrict__ ent, uint32_t *__restrict__ lists)
+{
+    __shared__ uint32_t s_pix[kCandTile];                 // candidate pixel index | hit mask << 24 is too narrow: two arrays
+    __shared__ uint8_t s_hit[kCandTile];
+    __shared__ uint32_t s_cnt, warp_tot[8];
+    __shared__ float s_lo[kMaxT], s_hi[kMaxT];
+    const uint32_t n_all = st->n;
+    if (n_all == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // ---- select inside the 10-bit histograms: 22-bit fast-key bin per target -> candidate band
+    for (int t = 0; t < T; ++t) {
+        int owner = t;
+        for (int u = t - 1; u >= 0; --u) if (st->prefix[u] == st->prefix[t]) owner = u;
+        const uint32_t *h = hist2 + owner * kBinsR;
+        const uint32_t c0 = __ldg(h + 4 * tid), c1 = __ldg(h + 4 * tid + 1), c2 = __ldg(h + 4 * tid + 2), c3 = __ldg(h + 4 * tid + 3);
+        const uint32_t sum = c0 + c1 + c2 + c3;
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < wid; ++w) base += warp_tot[w];
+        const uint32_t excl = base + inc - sum, r = st->rank[t];
+        if (r >= excl && r < excl + sum) {
+            const uint32_t cc[4] = {c0, c1, c2, c3};
+            uint32_t cum = excl;
+            int bin = 4 * tid;
+            for (int j = 0; j < 4; ++j) { if (r < cum + cc[j]) { bin = 4 * tid + j; break; } cum += cc[j]; }
+            const uint32_t pre = (st->prefix[t] << 10) | static_cast<uint32_t>(bin);
+            s_lo[t] = key_float(pre << 10) - 3.0f * kDelta;
+            s_hi[t] = (pre == 0x3FFFFFu) ? __uint_as_float(0x7f800000u) : key_float((pre + 1u) << 10) + 3.0f * kDelta;
+        }
+        __syncthreads();
+    }
+    float lo[kMaxT], hi[kMaxT];
+    uint32_t below[kMaxT];
+#pragma unroll
+    for (int t = 0; t < kMaxT; ++t) {
+        below[t] = 0;
+        lo[t] = (t < T) ? s_lo[t] : __uint_as_float(0x7f800000u);
+        hi[t] = (t < T) ? s_hi[t] : lo[t];
+    }
+    for (uint32_t base = blockIdx.x * kCandTile; base < N; base += gridDim.x * kCandTile) {
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        // ---- phase 1: band test on the fast keys (16 per thread)
+#pragma unroll 4
+        for (int it = 0; it < kCandTile / 256; ++it) {
+            const uint32_t i = base + it * 256 + tid;
+            const uint32_t k = (i < N) ? __ldg(keys + i) : kInvalidKey;
+            if (k == kInvalidKey) continue;
+            const float h = key_float(k);
+            uint32_t hit = 0;
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) {
+                if (t < T) {
+                    if (h < lo[t]) ++below[t];
+                    else if (h < hi[t]) hit |= (1u << t);
+                }
+            }
+            if (hit) {
+                const uint32_t pos = atomicAdd(&s_cnt, 1u);
+                s_pix[pos] = i;
+                s_hit[pos] = static_cast<uint8_t>(hit);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: exact (contract) entropy of the candidates, one per thread
+        const uint32_t nc = s_cnt;
+        for (uint32_t j = tid; j < nc; j += 256) {
+            const uint32_t i = s_pix[j];
+            uint32_t hit = s_hit[j];
+            const uint32_t b = i / HW, p = i - b * HW;
+            const float *x = logits + static_cast<size_t>(b) * C * HW + p;
+            float v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
+            const float e = entropy_of<C>(v);
+            ent[i] = e;
+            const uint32_t ek = float_key(e);
+            while (hit) {
+                const int t = __ffs(hit) - 1;
+                hit &= hit - 1;
+                const uint32_t pos = atomicAdd(&st->cnt[t], 1u);
+                lists[static_cast<size_t>(t) * N + pos] = ek;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int t = 0; t < kMaxT; ++t) {
+        if (t < T) {
+            const uint32_t sm = static_cast<uint32_t>(warp_sum_i(static_cast<int>(below[t])));
+            if (lane == 0 && sm) atomicAdd(&st->below[t], sm);
+        }
     }
 }
 
@@ -781,20 +952,13 @@ extern "C" int u2pl_entropy_thresholds_fast(const float *logits, const int64_t *
         const int g = grid_for(reinterpret_cast<const void *>(entropy_fast_hist_kernel<21>), kEntThreads, 0, N);
         entropy_fast_hist_kernel<21><<<g, kEntThreads, 0, s>>>(logits, target, hw, N, ignore, entropy, w.keys, w.hist1);
     }
-    select1_kernel<<<1, 256, 0, s>>>(w.hist1, w.st, pc, nq);
     const size_t smem = static_cast<size_t>(T) * kBinsR * 4;
-    const int g2 = grid_for(reinterpret_cast<const void *>(hist_refine_kernel<2>), 256, smem, N, 4);
-    hist_refine_kernel<2><<<g2, 256, smem, s>>>(w.keys, N, w.st, w.hist2, T);
-    select_refine_kernel<false><<<1, 1024, 0, s>>>(w.hist2, w.st, nq, thresh, nullptr);
-    if (C == 19) {
-        const int g = grid_for(reinterpret_cast<const void *>(candidate_kernel<19>), 256, 0, N);
-        candidate_kernel<19><<<g, 256, 0, s>>>(logits, w.keys, hw, N, w.st, T, entropy, lists);
-    } else {
-        const int g = grid_for(reinterpret_cast<const void *>(candidate_kernel<21>), 256, 0, N);
-        candidate_kernel<21><<<g, 256, 0, s>>>(logits, w.keys, hw, N, w.st, T, entropy, lists);
-    }
+    fast_refine_kernel<<<2 * kNumSMs, 256, smem, s>>>(w.keys, N, w.hist1, w.st, pc, nq, w.hist2);
+    const int gc = static_cast<int>(std::min<long long>((static_cast<long long>(N) + kCandTile - 1) / kCandTile, 4LL * kNumSMs));
+    if (C == 19) fast_candidate_kernel<19><<<gc, 256, 0, s>>>(logits, w.keys, hw, N, w.hist2, w.st, T, entropy, lists);
+    else         fast_candidate_kernel<21><<<gc, 256, 0, s>>>(logits, w.keys, hw, N, w.hist2, w.st, T, entropy, lists);
     exact_select_kernel<<<T, 1024, 0, s>>>(lists, N, w.st, nq, thresh, n_valid);
-    return check_launch("entropy_thresholds_fast", 6);
+    return check_launch("entropy_thresholds_fast", 4);
 }
 
 extern "C" int u2pl_partition_target(const float *entropy, int64_t *target, int64_t n, int64_t ignore,
