@@ -35,6 +35,7 @@ struct SelState {
     uint32_t cnt[kMaxT];            // two-level path: candidates gathered per target
     uint32_t below[kMaxT];          //                 valid pixels surely below the candidate band
     float    val[kMaxT];            //                 exact order statistics
+    uint32_t band[kMaxT];           //                 candidate band (list / counter index) of every target
 };
 
 struct Percents { float q[kMaxQ]; int use_rank; uint32_t rank; };   // use_rank: one explicit order statistic instead
@@ -424,9 +425,10 @@ exact_select_kernel(const uint32_t *__restrict__ lists, uint32_t N, SelState *__
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t n_all = st->n;
     if (n_all != 0) {
-        const uint32_t n = st->cnt[t];
-        const uint32_t r0 = st->grank[t] - st->below[t];              // unsigned: a violated invariant shows as r0 >= n
-        const uint32_t *list = lists + static_cast<size_t>(t) * N;
+        const uint32_t u = st->band[t];
+        const uint32_t n = st->cnt[u];
+        const uint32_t r0 = st->grank[t] - st->below[u];              // unsigned: a violated invariant shows as r0 >= n
+        const uint32_t *list = lists + static_cast<size_t>(u) * N;
         if (r0 >= n) {
             if (tid == 0) st->val[t] = __uint_as_float(0x7fc00000u);
         } else {
@@ -565,15 +567,13 @@ fast_refine_kernel(const uint32_t *__restrict__ keys, uint32_t N, const uint32_t
         for (int j = 0; j < nq; ++j) st->gamma[j] = s_gamma[j];
     }
     if (n == 0) return;
-    uint32_t pre[kMaxT];
-    uint32_t own_mask = 0;                                // targets that own a histogram (first of equal prefixes)
+    uint32_t pre[kMaxT];                                  // targets with equal prefixes share the first one's histogram
 #pragma unroll
     for (int t = 0; t < kMaxT; ++t) {
         pre[t] = (t < T) ? s_prefix[t] : kInvalidKey;
-        bool dup = false;
 #pragma unroll
-        for (int u = 0; u < t; ++u) dup = dup || (t < T && pre[u] == pre[t]);
-        if (t < T && !dup) own_mask |= (1u << t);
+        for (int u = 0; u < t; ++u)
+            if (t < T && s_prefix[u] == s_prefix[t]) pre[t] = kInvalidKey;     // key >> 20 never equals 0xFFFFFFFF
     }
     __syncthreads();
     const uint32_t n4 = N >> 2;
@@ -589,7 +589,7 @@ fast_refine_kernel(const uint32_t *__restrict__ keys, uint32_t N, const uint32_t
             const uint32_t hi = key >> 20;
             uint32_t mt = 0;
 #pragma unroll
-            for (int t = 0; t < kMaxT; ++t) mt |= (((own_mask >> t) & 1u) && hi == pre[t]) ? (1u << t) : 0u;
+            for (int t = 0; t < kMaxT; ++t) mt |= (hi == pre[t]) ? (1u << t) : 0u;
             if (mt) {
                 const uint32_t bin = (key >> 10) & (kBinsR - 1);
                 const uint32_t peers = __match_any_sync(__activemask(), (mt << 10) | bin);
@@ -613,14 +613,15 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
                       const uint32_t *__restrict__ hist2, SelState *__restrict__ st, int T,
                       float *__restrict__ ent, uint32_t *__restrict__ lists)
 {
-    __shared__ uint32_t s_pix[kCandTile];                 // candidate pixel index | hit mask << 24 is too narrow: two arrays
-    __shared__ uint8_t s_hit[kCandTile];
-    __shared__ uint32_t s_cnt, warp_tot[8];
+    __shared__ uint32_t s_pix[kCandTile];                 // candidates of the current tile: pixel index ...
+    __shared__ uint8_t s_hit[kCandTile];                  // ... and the bands it falls into
+    __shared__ uint32_t s_cnt, warp_tot[8], s_pre22[kMaxT], s_below[kMaxT], s_band[kMaxT];
     __shared__ float s_lo[kMaxT], s_hi[kMaxT];
+    __shared__ int s_nband;
     const uint32_t n_all = st->n;
     if (n_all == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // ---- select inside the 10-bit histograms: 22-bit fast-key bin per target -> candidate band
+    // ---- select inside the 10-bit histograms: 22-bit fast-key bin per target
     for (int t = 0; t < T; ++t) {
         int owner = t;
         for (int u = t - 1; u >= 0; --u) if (st->prefix[u] == st->prefix[t]) owner = u;
@@ -643,19 +644,37 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
             uint32_t cum = excl;
             int bin = 4 * tid;
             for (int j = 0; j < 4; ++j) { if (r < cum + cc[j]) { bin = 4 * tid + j; break; } cum += cc[j]; }
-            const uint32_t pre = (st->prefix[t] << 10) | static_cast<uint32_t>(bin);
-            s_lo[t] = key_float(pre << 10) - 3.0f * kDelta;
-            s_hi[t] = (pre == 0x3FFFFFu) ? __uint_as_float(0x7f800000u) : key_float((pre + 1u) << 10) + 3.0f * kDelta;
+            s_pre22[t] = (st->prefix[t] << 10) | static_cast<uint32_t>(bin);
         }
         __syncthreads();
     }
+    // ---- merge targets with the same bin into one candidate band (lo/hi ranks of a percentile, repeated percentiles)
+    if (tid == 0) {
+        int nb = 0;
+        for (int t = 0; t < T; ++t) {
+            int b = -1;
+            for (int u = 0; u < t; ++u) if (s_pre22[u] == s_pre22[t]) { b = static_cast<int>(s_band[u]); break; }
+            if (b < 0) {
+                b = nb++;
+                const uint32_t pre = s_pre22[t];
+                s_lo[b] = key_float(pre << 10) - 3.0f * kDelta;
+                s_hi[b] = (pre == 0x3FFFFFu) ? __uint_as_float(0x7f800000u) : key_float((pre + 1u) << 10) + 3.0f * kDelta;
+            }
+            s_band[t] = static_cast<uint32_t>(b);
+            if (blockIdx.x == 0) st->band[t] = static_cast<uint32_t>(b);
+        }
+        s_nband = nb;
+    }
+    if (tid < kMaxT) s_below[tid] = 0;
+    __syncthreads();
+    const int U = s_nband;
     float lo[kMaxT], hi[kMaxT];
     uint32_t below[kMaxT];
 #pragma unroll
-    for (int t = 0; t < kMaxT; ++t) {
-        below[t] = 0;
-        lo[t] = (t < T) ? s_lo[t] : __uint_as_float(0x7f800000u);
-        hi[t] = (t < T) ? s_hi[t] : lo[t];
+    for (int u = 0; u < kMaxT; ++u) {
+        below[u] = 0;
+        lo[u] = (u < U) ? s_lo[u] : __uint_as_float(0xff800000u);     // -inf: never below, never inside
+        hi[u] = (u < U) ? s_hi[u] : lo[u];
     }
     for (uint32_t base = blockIdx.x * kCandTile; base < N; base += gridDim.x * kCandTile) {
         if (tid == 0) s_cnt = 0;
@@ -669,11 +688,9 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
             const float h = key_float(k);
             uint32_t hit = 0;
 #pragma unroll
-            for (int t = 0; t < kMaxT; ++t) {
-                if (t < T) {
-                    if (h < lo[t]) ++below[t];
-                    else if (h < hi[t]) hit |= (1u << t);
-                }
+            for (int u = 0; u < kMaxT; ++u) {
+                below[u] += (h < lo[u]) ? 1u : 0u;
+                hit |= (h >= lo[u] && h < hi[u]) ? (1u << u) : 0u;
             }
             if (hit) {
                 const uint32_t pos = atomicAdd(&s_cnt, 1u);
@@ -696,21 +713,22 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
             ent[i] = e;
             const uint32_t ek = float_key(e);
             while (hit) {
-                const int t = __ffs(hit) - 1;
+                const int u = __ffs(hit) - 1;
                 hit &= hit - 1;
-                const uint32_t pos = atomicAdd(&st->cnt[t], 1u);
-                lists[static_cast<size_t>(t) * N + pos] = ek;
+                const uint32_t pos = atomicAdd(&st->cnt[u], 1u);
+                lists[static_cast<size_t>(u) * N + pos] = ek;
             }
         }
         __syncthreads();
     }
+    // one global atomic per band per BLOCK (all blocks hit the same addresses)
 #pragma unroll
-    for (int t = 0; t < kMaxT; ++t) {
-        if (t < T) {
-            const uint32_t sm = static_cast<uint32_t>(warp_sum_i(static_cast<int>(below[t])));
-            if (lane == 0 && sm) atomicAdd(&st->below[t], sm);
-        }
+    for (int u = 0; u < kMaxT; ++u) {
+        const uint32_t sm = static_cast<uint32_t>(warp_sum_i(static_cast<int>(below[u])));
+        if (lane == 0 && sm) atomicAdd(&s_below[u], sm);
     }
+    __syncthreads();
+    if (tid < U && s_below[tid]) atomicAdd(&st->below[tid], s_below[tid]);
 }
 
 // ------------------------------------------------------------------ OHEM (loss_helper.py:502-531)
@@ -953,7 +971,7 @@ extern "C" int u2pl_entropy_thresholds_fast(const float *logits, const int64_t *
         entropy_fast_hist_kernel<21><<<g, kEntThreads, 0, s>>>(logits, target, hw, N, ignore, entropy, w.keys, w.hist1);
     }
     const size_t smem = static_cast<size_t>(T) * kBinsR * 4;
-    fast_refine_kernel<<<2 * kNumSMs, 256, smem, s>>>(w.keys, N, w.hist1, w.st, pc, nq, w.hist2);
+    fast_refine_kernel<<<4 * kNumSMs, 256, smem, s>>>(w.keys, N, w.hist1, w.st, pc, nq, w.hist2);
     const int gc = static_cast<int>(std::min<long long>((static_cast<long long>(N) + kCandTile - 1) / kCandTile, 4LL * kNumSMs));
     if (C == 19) fast_candidate_kernel<19><<<gc, 256, 0, s>>>(logits, w.keys, hw, N, w.hist2, w.st, T, entropy, lists);
     else         fast_candidate_kernel<21><<<gc, 256, 0, s>>>(logits, w.keys, hw, N, w.hist2, w.st, T, entropy, lists);
