@@ -317,10 +317,18 @@ def our_arm(args):
     N = bu * crop * crop
     alg_bytes = (4 * C + 25) * N                                # (4C+25) B/pixel, entropy-partition
     ep = float(np.median(ep_us)) if ep_us else None
-    roofline = {"bound": "hbm", "kernel": "entropy_hist + radix-select chain + partition (u2pl_entropy_thresholds + "
-                "u2pl_partition_target), CUDA events inside the timed region",
+    traffic = None                                              # dram bytes of the dominant kernel from one `ncu --set full`
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            traffic = json.load(fh).get("entropy_fast_hist_kernel_dram_bytes")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "fused entropy / percentile / partition chain (u2pl_entropy_thresholds_fast: "
+                "entropy_fast_hist, fast_refine, fast_candidate, exact_select; + u2pl_partition_target), 3 percentiles, "
+                "CUDA events on the launching stream inside the timed step",
                 "achieved": (alg_bytes / (ep * 1e-6) / 1e9) if ep else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": (alg_bytes / (ep * 1e-6) / 1e9 / peaks["hbm_gbs"]) if ep else None, "traffic": None,
+                "frac": (alg_bytes / (ep * 1e-6) / 1e9 / peaks["hbm_gbs"]) if ep else None, "traffic": traffic,
+                "traffic_note": "dram read+write of entropy_fast_hist (the dominant kernel of the chain) per launch",
                 "us_per_call": ep, "algorithmic_bytes": alg_bytes, "peak_source": peaks["src"]}
     flop_step = FWD_GFLOP_PER_IMG.get(crop, 651.1) * 1e9 * (bu + 3 * (bl + bu) + (bl + bu))   # T1 + S fwd+bwd(2x) + T2
     tensor = {"bound": "tensor", "scope": "whole step (network = 3 passes)", "achieved": flop_step / (ms_step * 1e-3) / 1e12,
@@ -338,7 +346,8 @@ def our_arm(args):
             "config": {"workload": f"train_semi.py U2PL step (VOC-style), {arch}-DeepLabv3+ {crop}x{crop} C={C}, "
                                    f"{bl}+{bu} crops per GPU, epoch {EPOCH}/80, banks full (30k/50k x 256)",
                        "global_batch": imgs, "parallelism": f"dp{world}", "l2": "inputs_exceed_L2",
-                       "network": "channels-last bf16 autocast via cuDNN (library); losses fp32 via libu2pl_b200.so",
+                       "network": "channels-last bf16 autocast: convs via cuDNN/cuBLAS (library), BN+ReLU+residual and all "
+                                  "losses via libu2pl_b200.so",
                        "classifier_peak_scale": PEAK},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": 12 * world, "ms_per_step": ms_e2e},

@@ -255,9 +255,9 @@ proto_partial_kernel(const float *__restrict__ feat, long long sn, long long sd,
     __shared__ uint32_t s_any;
     for (uint32_t j = threadIdx.x; j < C * D; j += 256) acc[j] = 0.0f;
     const uint32_t ntiles = (P + 31) / 32;
-    const uint32_t per = (ntiles + gridDim.x - 1) / gridDim.x;
-    const uint32_t t0 = blockIdx.x * per, t1 = min(t0 + per, ntiles);
-    for (uint32_t t = t0; t < t1; ++t) {
+    // tiles are dealt round-robin: with the reference's label_onehot quirk only image 0 of each half of the
+    // batch has members, and contiguous ranges would leave that work to a handful of blocks
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         __syncthreads();
         if (threadIdx.x < 32) {
             const uint32_t pix = t * 32 + threadIdx.x;
@@ -476,13 +476,18 @@ infonce_fwd_kernel(InfoNceArgs a)
     for (int j = 0; j < 8; ++j) { V[j] = 0.0f; K0[j] = 0.0f; }
     const int32_t *rows = a.neg_rows + static_cast<size_t>(w) * a.nneg;
     const bool c0 = d0 < a.D, c1 = d1 < a.D;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *kr0 = a.proto + static_cast<size_t>(cls) * a.D;
+    float4 n0 = c0 ? __ldg(reinterpret_cast<const float4 *>(kr0 + d0)) : z4;      // row t+1 is in flight while row t is reduced
+    float4 n1 = c1 ? __ldg(reinterpret_cast<const float4 *>(kr0 + d1)) : z4;
     for (int t = 0; t <= a.nneg; ++t) {
-        const float *kr = (t == 0) ? a.proto + static_cast<size_t>(cls) * a.D
-                                   : a.bank + static_cast<size_t>(__ldg(rows + t - 1)) * a.D;
+        const float4 x0 = n0, x1 = n1;
+        if (t < a.nneg) {
+            const float *kn_ = a.bank + static_cast<size_t>(__ldg(rows + t)) * a.D;
+            n0 = c0 ? __ldg(reinterpret_cast<const float4 *>(kn_ + d0)) : z4;
+            n1 = c1 ? __ldg(reinterpret_cast<const float4 *>(kn_ + d1)) : z4;
+        }
         float kv[8];
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 x0 = c0 ? __ldg(reinterpret_cast<const float4 *>(kr + d0)) : z4;
-        const float4 x1 = c1 ? __ldg(reinterpret_cast<const float4 *>(kr + d1)) : z4;
         kv[0] = x0.x; kv[1] = x0.y; kv[2] = x0.z; kv[3] = x0.w;
         kv[4] = x1.x; kv[5] = x1.y; kv[6] = x1.z; kv[7] = x1.w;
         float dot = 0.0f, kn = 0.0f;
