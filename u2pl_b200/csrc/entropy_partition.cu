@@ -377,7 +377,8 @@ __device__ __forceinline__ float entropy_fast_of(float (&v)[C])
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const float d = v[c] - m;
-        const float e = exp2f(d * 1.4426950408889634f);
+        float e;                                           // MUFU.EX2 directly (exp2f adds denormal-range handling)
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(d * 1.4426950408889634f));
         S += e;
         Wd = fmaf(e, d, Wd);
     }
