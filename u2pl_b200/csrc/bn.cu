@@ -157,19 +157,49 @@ bn_fold_kernel(int C, const float *__restrict__ gamma, const float *__restrict__
     shift[c] = b - running_mean[c] * g * invstd;
 }
 
+// Thread (slot, cvec) owns the same 8 channels for every row it visits, so scale / shift sit in registers
+// and each 16-byte activation vector costs one load (+1 for the residual) and one store.
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ res, const float *__restrict__ scale,
-                const float *__restrict__ shift, long long nvec, int tpr, int relu, uint4 *__restrict__ y)
+                const float *__restrict__ shift, long long M, int tpr, int relu, uint4 *__restrict__ y)
 {
-    for (long long i = static_cast<long long>(blockIdx.x) * kBnThreads + threadIdx.x; i < nvec;
-         i += static_cast<long long>(gridDim.x) * kBnThreads) {
-        const int cvec = static_cast<int>(i % tpr);
-        float v[8], sc[8], sh[8];
+    const int slots = kBnThreads / tpr, slot = threadIdx.x / tpr, cvec = threadIdx.x - slot * tpr;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + cvec * 8 + j); sh[j] = __ldg(shift + cvec * 8 + j); }
+    const long long step = static_cast<long long>(gridDim.x) * slots;
+    long long row = static_cast<long long>(blockIdx.x) * slots + slot;
+    for (; row + 3 * step < M; row += 4 * step) {                     // 4 (8 with residual) independent loads in flight
+        uint4 xv[4], rv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = (row + u * step) * tpr + cvec;
+            xv[u] = __ldg(x + i);
+            if (res) rv[u] = __ldg(res + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v[8];
+            unpack8(xv[u], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+            if (res) {
+                float r[8];
+                unpack8(rv[u], r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += r[j];
+            }
+            if (relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+            y[(row + u * step) * tpr + cvec] = pack8(v);
+        }
+    }
+    for (; row < M; row += step) {
+        const long long i = row * tpr + cvec;
+        float v[8];
         unpack8(__ldg(x + i), v);
-        *reinterpret_cast<float4 *>(sc) = __ldg(reinterpret_cast<const float4 *>(scale) + cvec * 2);
-        *reinterpret_cast<float4 *>(sc + 4) = __ldg(reinterpret_cast<const float4 *>(scale) + cvec * 2 + 1);
-        *reinterpret_cast<float4 *>(sh) = __ldg(reinterpret_cast<const float4 *>(shift) + cvec * 2);
-        *reinterpret_cast<float4 *>(sh + 4) = __ldg(reinterpret_cast<const float4 *>(shift) + cvec * 2 + 1);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
         if (res) {
@@ -255,15 +285,44 @@ bn_bwd_coef_kernel(const float *__restrict__ mean, const float *__restrict__ inv
 
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_elemt_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, const uint4 *__restrict__ y,
-                    const float *__restrict__ coef, long long nvec, int C, uint4 *__restrict__ dx, uint4 *__restrict__ dres)
+                    const float *__restrict__ coef, long long M, int C, uint4 *__restrict__ dx, uint4 *__restrict__ dres)
 {
-    const int tpr = C >> 3;
-    const float4 *cA = reinterpret_cast<const float4 *>(coef), *cB = reinterpret_cast<const float4 *>(coef + C),
-                 *cD = reinterpret_cast<const float4 *>(coef + 2 * C);
-    for (long long i = static_cast<long long>(blockIdx.x) * kBnThreads + threadIdx.x; i < nvec;
-         i += static_cast<long long>(gridDim.x) * kBnThreads) {
-        const int cv = static_cast<int>(i % tpr) * 2;
-        float g[8], xv[8], o[8], A[8], B[8], D[8];
+    const int tpr = C >> 3, slots = kBnThreads / tpr, slot = threadIdx.x / tpr, cvec = threadIdx.x - slot * tpr;
+    float A[8], B[8], D[8];                                            // per-channel coefficients live in registers
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        A[j] = __ldg(coef + cvec * 8 + j);
+        B[j] = __ldg(coef + C + cvec * 8 + j);
+        D[j] = __ldg(coef + 2 * C + cvec * 8 + j);
+    }
+    const long long step = static_cast<long long>(gridDim.x) * slots;
+    long long row = static_cast<long long>(blockIdx.x) * slots + slot;
+    for (; row + step < M; row += 2 * step) {                          // two rows = 4-6 independent 16 B loads in flight
+        const long long i0 = row * tpr + cvec, i1 = (row + step) * tpr + cvec;
+        const uint4 a0 = __ldg(dy + i0), b0 = __ldg(x + i0), a1 = __ldg(dy + i1), b1 = __ldg(x + i1);
+        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+        if (y) { c0 = __ldg(y + i0); c1 = __ldg(y + i1); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float g[8], xv[8], o[8];
+            unpack8(u ? a1 : a0, g);
+            unpack8(u ? b1 : b0, xv);
+            if (y) {
+                float yv[8];
+                unpack8(u ? c1 : c0, yv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.0f ? g[j] : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], g[j], fmaf(B[j], xv[j], D[j]));
+            const long long i = u ? i1 : i0;
+            dx[i] = pack8(o);
+            if (dres) dres[i] = pack8(g);
+        }
+    }
+    for (; row < M; row += step) {
+        const long long i = row * tpr + cvec;
+        float g[8], xv[8], o[8];
         unpack8(__ldg(dy + i), g);
         unpack8(__ldg(x + i), xv);
         if (y) {
@@ -272,9 +331,6 @@ bn_bwd_elemt_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, c
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.0f ? g[j] : 0.0f;
         }
-        *reinterpret_cast<float4 *>(A) = __ldg(cA + cv); *reinterpret_cast<float4 *>(A + 4) = __ldg(cA + cv + 1);
-        *reinterpret_cast<float4 *>(B) = __ldg(cB + cv); *reinterpret_cast<float4 *>(B + 4) = __ldg(cB + cv + 1);
-        *reinterpret_cast<float4 *>(D) = __ldg(cD + cv); *reinterpret_cast<float4 *>(D + 4) = __ldg(cD + cv + 1);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], g[j], fmaf(B[j], xv[j], D[j]));
         dx[i] = pack8(o);
@@ -333,8 +389,8 @@ extern "C" int u2pl_bn_apply(const void *x, const void *residual, const float *s
 {
     if (!bn_shape_ok(M, C)) return bad_arg("bn_apply: unsupported channel count");
     const long long nvec = M * (C / 8);
-    bn_apply_kernel<<<bn_grid(nvec), kBnThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4 *>(x), static_cast<const uint4 *>(residual), scale, shift, nvec, static_cast<int>(C / 8), relu,
+    bn_apply_kernel<<<bn_grid(nvec / 2), kBnThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4 *>(x), static_cast<const uint4 *>(residual), scale, shift, M, static_cast<int>(C / 8), relu,
         static_cast<uint4 *>(y));
     return check_launch("bn_apply");
 }
@@ -360,8 +416,8 @@ extern "C" int u2pl_bn_backward_elemt(const void *dy, const void *x, const void 
     const long long nvec = M * (C / 8);
     bn_bwd_coef_kernel<<<static_cast<int>((C + 255) / 256), 256, 0, s>>>(mean, invstd, gamma, sums, static_cast<float>(1.0 / count),
                                                                        static_cast<int>(C), coef);
-    bn_bwd_elemt_kernel<<<bn_grid(nvec), kBnThreads, 0, s>>>(static_cast<const uint4 *>(dy), static_cast<const uint4 *>(x),
-                                                             static_cast<const uint4 *>(y), coef, nvec, static_cast<int>(C),
+    bn_bwd_elemt_kernel<<<bn_grid(nvec / 2), kBnThreads, 0, s>>>(static_cast<const uint4 *>(dy), static_cast<const uint4 *>(x),
+                                                                 static_cast<const uint4 *>(y), coef, M, static_cast<int>(C),
                                                              static_cast<uint4 *>(dx), static_cast<uint4 *>(dres));
     return check_launch("bn_backward_elemt", 2);
 }
