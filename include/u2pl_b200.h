@@ -242,6 +242,16 @@ int u2pl_bn_backward_elemt(const void *dy, const void *x, const void *y, const f
                            const float *gamma, const float *sums, double count, int64_t M, int64_t C,
                            float *coef /* scratch [3][C] */, void *dx, void *dres, void *stream);
 
+/* ------------------------------------------------------------------------
+ * A1  1x1 convolution as a tensor-core GEMM (tcgen05 + TMA), optional folded-BN + ReLU epilogue
+ * replaces: conv1x1 (resnet.py:39-41) [+ eval-mode BatchNorm + ReLU] on channels-last activations.
+ *   D[M,N] = act( (A[M,K] . B[N,K]^T) * scale[n] + shift[n] ),  A/B/D bf16 row-major, fp32 accumulation;
+ *   scale/shift fp32 (NULL: plain product), relu != 0 applies max(.,0).  K % 8 == 0, N % 8 == 0,
+ *   pointers 16-byte aligned.  M = N*H*W pixels, K = Cin, N = Cout.
+ * ---------------------------------------------------------------------- */
+int u2pl_gemm_bf16_tn(const void *A, const void *B, void *D, int64_t M, int64_t N, int64_t K,
+                      const float *scale, const float *shift, int relu, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

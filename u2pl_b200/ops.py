@@ -256,3 +256,28 @@ def ohem_cross_entropy(pred, target, thresh, min_kept, ignore=255):
     """OhemCrossEntropy2dTensor.forward (loss_helper.py:502-531): mean CE over the kept pixels."""
     new_target, _, _ = ohem_select(pred, target, thresh, min_kept, ignore)
     return cross_entropy_mean(pred, new_target, ignore)
+
+
+# --------------------------------------------------------------------------- tcgen05 GEMM (1x1 conv)
+def gemm_bf16_tn(a, b, scale=None, shift=None, relu=False):
+    """D = act((a @ b.T) * scale + shift): a [M,K], b [N,K] bf16 row-major -> D [M,N] bf16 (csrc/gemm_tc.cu)."""
+    _need_cuda(a, b, scale, shift)
+    lib = _lib.load()
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K
+    d = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    rc = lib.u2pl_gemm_bf16_tn(_p(a), _p(b), _p(d), M, N, K, _p(scale), _p(shift), int(bool(relu)), _stream())
+    _lib.check(rc, "u2pl_gemm_bf16_tn")
+    return d
+
+
+def conv1x1_bn_relu_eval(x, weight, scale, shift, relu=True):
+    """conv1x1 + folded eval-mode BatchNorm + ReLU on a channels-last bf16 activation [N,Cin,H,W]."""
+    N, Cin, H, W = x.shape
+    assert x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16
+    a = x.permute(0, 2, 3, 1).reshape(N * H * W, Cin)            # view: NHWC is the physical layout
+    w = weight.reshape(weight.shape[0], Cin).to(torch.bfloat16).contiguous()
+    d = gemm_bf16_tn(a, w, scale, shift, relu)
+    return d.view(N, H, W, -1).permute(0, 3, 1, 2)               # channels-last view of [N,Cout,H,W]
