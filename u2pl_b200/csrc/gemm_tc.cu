@@ -89,6 +89,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t *empty = full + kStages;
     uint64_t *tmem_full = empty + kStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    float *s_scale = reinterpret_cast<float *>(tmem_slot + 2), *s_shift = s_scale + kBN;   // epilogue parameters of this tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
@@ -141,6 +142,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     } else {                                          // ---------------- epilogue (warps 2..5)
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        {                                             // stage the tile's 128 scale / shift values once (smem broadcast reads later)
+            const int e = threadIdx.x - 64, c = n0 + e;
+            s_scale[e] = (p.scale && c < p.N) ? __ldg(p.scale + c) : 1.0f;
+            s_shift[e] = (p.shift && c < p.N) ? __ldg(p.shift + c) : 0.0f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+        }
+        const bool affine = p.scale != nullptr || p.shift != nullptr;
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + q * 32 + lane;
@@ -168,7 +176,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             float x = __uint_as_float(r[g * 8 + e]);
-                            if (p.scale) x = fmaf(x, __ldg(p.scale + c + e), p.shift ? __ldg(p.shift + c + e) : 0.0f);
+                            if (affine) x = fmaf(x, s_scale[j * 32 + g * 8 + e], s_shift[j * 32 + g * 8 + e]);
                             if (p.relu) x = fmaxf(x, 0.0f);
                             v[e] = x;
                         }
@@ -232,7 +240,7 @@ extern "C" int u2pl_gemm_bf16_tn(const void *A, const void *B, void *D, int64_t 
         return bad_arg("gemm_bf16_tn: operands must be 16-byte aligned");
     CUtensorMap ma, mb;
     if (!make_map(&ma, A, M, K, kBM) || !make_map(&mb, B, N, K, kBN)) { set_error("gemm_bf16_tn: cuTensorMapEncodeTiled failed"); return U2PL_E_BADARG; }
-    const size_t smem = static_cast<size_t>(kStages) * (kTileABytes + kTileBBytes) + 1024 + 256;
+    const size_t smem = static_cast<size_t>(kStages) * (kTileABytes + kTileBBytes) + 1024 + 256 + 2 * kBN * sizeof(float);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
