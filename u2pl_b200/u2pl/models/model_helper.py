@@ -1,48 +1,45 @@
-"""ModelBuilder: encoder / decoder / aux head resolved from dotted type strings (the reference's
-plugin API, u2pl/models/model_helper.py:9-66).  forward(x) -> {"pred", "rep"[, "aux"]}."""
-import importlib
+"""`ModelBuilder`: the reference's plugin API (u2pl/models/model_helper.py:9-66) -- encoder and decoder
+classes are named by dotted strings in the config and resolved with importlib; `forward(x)` returns
+{"pred", "rep"[, "aux"]}.  Attribute names (`encoder`, `decoder`, `auxor`) are part of the contract:
+train_semi.py:82-110 builds optimiser parameter groups from them."""
+from importlib import import_module
 
 import torch.nn as nn
 
 from .decoder import Aux_Module
 
 
+def _instantiate(dotted, kwargs):
+    module_path, _, attr = dotted.rpartition(".")
+    return getattr(import_module(module_path), attr)(**kwargs)
+
+
 class ModelBuilder(nn.Module):
     def __init__(self, net_cfg):
         super().__init__()
-        self._sync_bn = net_cfg["sync_bn"]
-        self._num_classes = net_cfg["num_classes"]
-        self.encoder = self._build_encoder(net_cfg["encoder"])
-        self.decoder = self._build_decoder(net_cfg["decoder"])
-        self._use_auxloss = bool(net_cfg.get("aux_loss", False))
-        self.fpn = bool(net_cfg["encoder"]["kwargs"].get("fpn", False))
-        if self._use_auxloss:
-            cfg_aux = net_cfg["aux_loss"]
-            self.loss_weight = cfg_aux["loss_weight"]
-            self.auxor = Aux_Module(cfg_aux["aux_plane"], self._num_classes, self._sync_bn)
+        sync_bn, classes = net_cfg["sync_bn"], net_cfg["num_classes"]
+        self._sync_bn, self._num_classes = sync_bn, classes
 
-    def _build_encoder(self, enc_cfg):
-        enc_cfg["kwargs"].update({"sync_bn": self._sync_bn})
-        return self._build_module(enc_cfg["type"], enc_cfg["kwargs"])
+        enc = net_cfg["encoder"]
+        enc["kwargs"]["sync_bn"] = sync_bn                      # the reference mutates the config dict in place too
+        self.encoder = _instantiate(enc["type"], enc["kwargs"])
 
-    def _build_decoder(self, dec_cfg):
-        dec_cfg["kwargs"].update({"in_planes": self.encoder.get_outplanes(), "sync_bn": self._sync_bn,
-                                  "num_classes": self._num_classes})
-        return self._build_module(dec_cfg["type"], dec_cfg["kwargs"])
+        dec = net_cfg["decoder"]
+        dec["kwargs"].update(in_planes=self.encoder.get_outplanes(), sync_bn=sync_bn, num_classes=classes)
+        self.decoder = _instantiate(dec["type"], dec["kwargs"])
 
-    @staticmethod
-    def _build_module(mtype, kwargs):
-        module_name, class_name = mtype.rsplit(".", 1)
-        return getattr(importlib.import_module(module_name), class_name)(**kwargs)
+        aux_cfg = net_cfg.get("aux_loss", False)
+        self._use_auxloss = bool(aux_cfg)
+        self.fpn = bool(enc["kwargs"].get("fpn", False))
+        if aux_cfg:
+            self.loss_weight = aux_cfg["loss_weight"]
+            self.auxor = Aux_Module(aux_cfg["aux_plane"], classes, sync_bn)
 
     def forward(self, x):
+        feats = self.encoder(x)
         if not self._use_auxloss:
-            return self.decoder(self.encoder(x))
-        if self.fpn:
-            f1, f2, feat1, feat2 = self.encoder(x)
-            outs = self.decoder([f1, f2, feat1, feat2])
-        else:
-            feat1, feat2 = self.encoder(x)
-            outs = self.decoder(feat2)
-        outs.update({"aux": self.auxor(feat1)})
+            return self.decoder(feats)
+        # with the aux head the decoder sees either the 4-level pyramid (fpn) or only the last stage
+        outs = self.decoder(list(feats) if self.fpn else feats[1])
+        outs["aux"] = self.auxor(feats[2] if self.fpn else feats[0])
         return outs

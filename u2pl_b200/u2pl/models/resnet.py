@@ -1,6 +1,12 @@
-"""ResNet-v1c encoders (deep 3x3 stem, ceil-mode max-pool, stride->dilation, multi-grid).
-Mirrors u2pl/models/resnet.py:25-402: same module tree, registration order and initialisation
-sequence, so a state_dict or a torch seed produces the same weights as the reference."""
+"""ResNet-v1c encoders (deep 3x3 stem, ceil-mode max-pool, stride->dilation, multi-grid) for the
+drop-in `u2pl.models.resnet.*` dotted types.
+
+Everything a checkpoint or a seeded construction can observe is kept identical to the reference
+(u2pl/models/resnet.py:25-402): module names and registration order, parameter order, the order in
+which convolutions are constructed (it fixes the RNG stream) and the re-initialisation pass.  The
+code itself is organised around two small tables (`_BLOCK_SPECS`, `_ARCHS`) instead of hand-written
+classes per variant, and the forward passes go through the fused BN(+ReLU+residual) kernels.
+"""
 import torch
 import torch.nn as nn
 
@@ -8,109 +14,109 @@ from u2pl_b200.fused import DilatedConv2d, StemConv2d, bn_act, run_sequential
 
 from .base import _norm
 
-__all__ = ["ResNet", "resnet18", "resnet34", "resnet50", "resnet101", "resnet152"]
-
-model_urls = {name: f"/path/to/{name}.pth" for name in ("resnet18", "resnet34", "resnet50", "resnet101", "resnet152")}
+model_urls = {f"resnet{d}": f"/path/to/resnet{d}.pth" for d in (18, 34, 50, 101, 152)}
 
 
 def conv3x3(cin, cout, stride=1, groups=1, dilation=1):
     # strided or strongly dilated 3x3 (layer2.0, layer4 d=4/8/16): GEMM-based weight gradient (fused.py);
     # cuDNN 9 falls back to wgrad_alg0_engine for some of them on B200 (18 ms for one 512->512 d=16 layer)
-    conv = DilatedConv2d if (stride != 1 or dilation >= 4) else nn.Conv2d
-    return conv(cin, cout, kernel_size=3, stride=stride, padding=dilation, groups=groups, bias=False,
-                dilation=dilation)
+    kind = DilatedConv2d if (stride != 1 or dilation >= 4) else nn.Conv2d
+    return kind(cin, cout, 3, stride, dilation, dilation, groups, False)
 
 
 def conv1x1(cin, cout, stride=1):
-    return nn.Conv2d(cin, cout, kernel_size=1, stride=stride, bias=False)
+    return nn.Conv2d(cin, cout, 1, stride, bias=False)
 
 
-class BasicBlock(nn.Module):
-    expansion = 1
+# (kernel, uses the block's stride/dilation?) for conv1..convN of each residual block type
+_BLOCK_SPECS = {"basic": (1, [(3, True), (3, False)]), "bottleneck": (4, [(1, False), (3, True), (1, False)])}
+
+
+class _Residual(nn.Module):
+    """conv/bn pairs named conv1, bn1, ... in the reference's registration order, then relu, downsample."""
+    kind = None
 
     def __init__(self, inplanes, planes, stride=1, downsample=None, groups=1, base_width=64, dilation=1,
                  norm_layer=None):
         super().__init__()
         norm_layer = norm_layer or nn.BatchNorm2d
-        if groups != 1 or base_width != 64:
-            raise ValueError("BasicBlock only supports groups=1 and base_width=64")
-        if dilation > 1:
-            raise NotImplementedError("Dilation > 1 not supported in BasicBlock")
-        self.conv1 = conv3x3(inplanes, planes, stride)
-        self.bn1 = norm_layer(planes)
-        self.relu = nn.ReLU(inplace=True)
-        self.conv2 = conv3x3(planes, planes)
-        self.bn2 = norm_layer(planes)
-        self.downsample = downsample
-        self.stride = stride
-
-    def forward(self, x):
-        y = bn_act(self.conv1(x), self.bn1, self.relu)
-        identity = x if self.downsample is None else run_sequential(self.downsample, x)
-        return bn_act(self.conv2(y), self.bn2, self.relu, residual=identity)
-
-
-class Bottleneck(nn.Module):
-    expansion = 4
-
-    def __init__(self, inplanes, planes, stride=1, downsample=None, groups=1, base_width=64, dilation=1,
-                 norm_layer=nn.BatchNorm2d):
-        super().__init__()
-        width = int(planes * (base_width / 64.0)) * groups
-        self.conv1 = conv1x1(inplanes, width)
-        self.bn1 = norm_layer(width)
-        self.conv2 = conv3x3(width, width, stride, groups, dilation)
-        self.bn2 = norm_layer(width)
-        self.conv3 = conv1x1(width, planes * self.expansion)
-        self.bn3 = norm_layer(planes * self.expansion)
+        expansion, convs = _BLOCK_SPECS[self.kind]
+        if self.kind == "basic":
+            if groups != 1 or base_width != 64:
+                raise ValueError("BasicBlock only supports groups=1 and base_width=64")
+            if dilation > 1:
+                raise NotImplementedError("Dilation > 1 not supported in BasicBlock")
+            widths = [planes, planes]
+        else:
+            inner = int(planes * (base_width / 64.0)) * groups
+            widths = [inner, inner, planes * expansion]
+        cin = inplanes
+        for i, ((k, strided), cout) in enumerate(zip(convs, widths), start=1):
+            if k == 1:
+                conv = conv1x1(cin, cout)
+            elif self.kind == "basic":
+                conv = conv3x3(cin, cout, stride if strided else 1)
+            else:
+                conv = conv3x3(cin, cout, stride, groups, dilation)
+            setattr(self, f"conv{i}", conv)
+            setattr(self, f"bn{i}", norm_layer(cout))
+            cin = cout
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
         self.stride = stride
+        self._depth = len(convs)
 
     def forward(self, x):
-        y = bn_act(self.conv1(x), self.bn1, self.relu)
-        y = bn_act(self.conv2(y), self.bn2, self.relu)
-        identity = x if self.downsample is None else run_sequential(self.downsample, x)
-        return bn_act(self.conv3(y), self.bn3, self.relu, residual=identity)      # relu(bn3(.) + identity)
+        shortcut = x if self.downsample is None else run_sequential(self.downsample, x)
+        y = x
+        for i in range(1, self._depth):
+            y = bn_act(getattr(self, f"conv{i}")(y), getattr(self, f"bn{i}"), self.relu)
+        last = self._depth
+        return bn_act(getattr(self, f"conv{last}")(y), getattr(self, f"bn{last}"), self.relu, residual=shortcut)
+
+
+class BasicBlock(_Residual):
+    kind, expansion = "basic", 1
+
+
+class Bottleneck(_Residual):
+    kind, expansion = "bottleneck", 4
 
 
 class ResNet(nn.Module):
     def __init__(self, block, layers, zero_init_residual=False, groups=1, width_per_group=64,
                  replace_stride_with_dilation=(False, False, False), sync_bn=False, multi_grid=False, fpn=False):
         super().__init__()
-        norm_layer = _norm(sync_bn)
-        self._norm_layer = norm_layer
-        self.inplanes, self.dilation = 128, 1
         if replace_stride_with_dilation is None:
-            replace_stride_with_dilation = [False, False, False]
+            replace_stride_with_dilation = (False, False, False)
         if len(replace_stride_with_dilation) != 3:
-            raise ValueError("replace_stride_with_dilation should be None or a 3-element tuple, "
-                             f"got {replace_stride_with_dilation}")
-        self.groups, self.base_width, self.fpn = groups, width_per_group, fpn
-        stem = StemConv2d(3, 64, kernel_size=3, stride=2, padding=1, bias=False, dilation=1)   # = conv3x3(3, 64, 2)
-        self.conv1 = nn.Sequential(stem, norm_layer(64), nn.ReLU(inplace=True),
-                                   conv3x3(64, 64), norm_layer(64), nn.ReLU(inplace=True),
-                                   conv3x3(64, self.inplanes))
-        self.bn1 = norm_layer(self.inplanes)
+            raise ValueError(f"replace_stride_with_dilation should be None or a 3-element tuple, got "
+                             f"{replace_stride_with_dilation}")
+        norm = self._norm_layer = _norm(sync_bn)
+        self.inplanes, self.dilation, self.groups, self.base_width, self.fpn = 128, 1, groups, width_per_group, fpn
+        stem = [StemConv2d(3, 64, 3, 2, 1, 1, 1, False), norm(64), nn.ReLU(inplace=True),       # == conv3x3(3, 64, 2)
+                conv3x3(64, 64), norm(64), nn.ReLU(inplace=True), conv3x3(64, self.inplanes)]
+        self.conv1 = nn.Sequential(*stem)
+        self.bn1 = norm(self.inplanes)
         self.relu = nn.ReLU(inplace=True)
-        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1, ceil_mode=True)
-        self.layer1 = self._make_layer(block, 64, layers[0])
-        self.layer2 = self._make_layer(block, 128, layers[1], stride=2, dilate=replace_stride_with_dilation[0])
-        self.layer3 = self._make_layer(block, 256, layers[2], stride=2, dilate=replace_stride_with_dilation[1])
-        self.layer4 = self._make_layer(block, 512, layers[3], stride=2, dilate=replace_stride_with_dilation[2],
-                                       multi_grid=multi_grid)
-        for m in self.modules():
+        self.maxpool = nn.MaxPool2d(3, 2, 1, ceil_mode=True)
+        stage_cfg = [(64, 1, False, False)] + [(128 << i, 2, bool(replace_stride_with_dilation[i]), multi_grid and i == 2)
+                                               for i in range(3)]
+        for idx, ((planes, stride, dilate, grid), depth) in enumerate(zip(stage_cfg, layers), start=1):
+            setattr(self, f"layer{idx}", self._make_layer(block, planes, depth, stride, dilate, grid))
+        self._reset_parameters(zero_init_residual)
+
+    def _reset_parameters(self, zero_init_residual):
+        for m in self.modules():                       # same traversal order as the reference (RNG stream)
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
             elif isinstance(m, (nn.BatchNorm2d, nn.GroupNorm, nn.SyncBatchNorm)):
-                nn.init.constant_(m.weight, 1)
-                nn.init.constant_(m.bias, 0)
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
         if zero_init_residual:
             for m in self.modules():
-                if isinstance(m, Bottleneck):
-                    nn.init.constant_(m.bn3.weight, 0)
-                elif isinstance(m, BasicBlock):
-                    nn.init.constant_(m.bn2.weight, 0)
+                if isinstance(m, _Residual):
+                    nn.init.zeros_(getattr(m, f"bn{m._depth}").weight)
 
     def get_outplanes(self):
         return self.inplanes
@@ -119,58 +125,49 @@ class ResNet(nn.Module):
         return self.inplanes // 2
 
     def _make_layer(self, block, planes, blocks, stride=1, dilate=False, multi_grid=False):
-        norm_layer = self._norm_layer
-        prev_dilation = self.dilation
+        first_dilation = self.dilation
         if dilate:
-            self.dilation *= stride
-            stride = 1
-        downsample = None
-        if stride != 1 or self.inplanes != planes * block.expansion:
-            downsample = nn.Sequential(conv1x1(self.inplanes, planes * block.expansion, stride),
-                                       norm_layer(planes * block.expansion))
+            self.dilation, stride = self.dilation * stride, 1
+        out_planes = planes * block.expansion
+        shortcut = None
+        if stride != 1 or self.inplanes != out_planes:
+            shortcut = nn.Sequential(conv1x1(self.inplanes, out_planes, stride), self._norm_layer(out_planes))
         grids = [2, 2, 4] if multi_grid else [1] * blocks
-        stack = [block(self.inplanes, planes, stride, downsample, self.groups, self.base_width,
-                       prev_dilation * grids[0], norm_layer)]
-        self.inplanes = planes * block.expansion
-        for i in range(1, blocks):
-            stack.append(block(self.inplanes, planes, groups=self.groups, base_width=self.base_width,
-                               dilation=self.dilation * grids[i], norm_layer=norm_layer))
+        common = dict(groups=self.groups, base_width=self.base_width, norm_layer=self._norm_layer)
+        stack = [block(self.inplanes, planes, stride, shortcut, dilation=first_dilation * grids[0], **common)]
+        self.inplanes = out_planes
+        stack += [block(out_planes, planes, dilation=self.dilation * grids[i], **common) for i in range(1, blocks)]
         return nn.Sequential(*stack)
 
     def forward(self, x):
         x = self.maxpool(bn_act(run_sequential(self.conv1, x), self.bn1, self.relu))
-        x1 = self.layer1(x)
-        x2 = self.layer2(x1)
-        x3 = self.layer3(x2)
-        x4 = self.layer4(x3)
-        return [x1, x2, x3, x4] if self.fpn else [x3, x4]
+        feats = []
+        for idx in range(1, 5):
+            x = getattr(self, f"layer{idx}")(x)
+            feats.append(x)
+        return feats if self.fpn else feats[2:]
 
 
-def _build(name, block, layers, pretrained, **kwargs):
-    model = ResNet(block, layers, **kwargs)
-    if pretrained:
-        state = torch.load(model_urls[name])
-        missing, unexpected = model.load_state_dict(state, strict=False)
-        print(f"[Info] Load ImageNet pretrain from '{model_urls[name]}'", "\nmissing_keys: ", missing,
-              "\nunexpected_keys: ", unexpected)
-    return model
+_ARCHS = {"resnet18": (BasicBlock, [2, 2, 2, 2], False), "resnet34": (BasicBlock, [3, 4, 6, 3], False),
+          "resnet50": (Bottleneck, [3, 4, 6, 3], True), "resnet101": (Bottleneck, [3, 4, 23, 3], True),
+          "resnet152": (Bottleneck, [3, 8, 36, 3], True)}
 
 
-def resnet18(pretrained=False, **kwargs):
-    return _build("resnet18", BasicBlock, [2, 2, 2, 2], pretrained, **kwargs)
+def _factory(name):
+    block, depths, pretrained_default = _ARCHS[name]
+
+    def build(pretrained=pretrained_default, **kwargs):
+        net = ResNet(block, depths, **kwargs)
+        if pretrained:
+            missing, unexpected = net.load_state_dict(torch.load(model_urls[name]), strict=False)
+            print(f"[Info] Load ImageNet pretrain from '{model_urls[name]}'", "\nmissing_keys: ", missing,
+                  "\nunexpected_keys: ", unexpected)
+        return net
+
+    build.__name__ = name
+    build.__doc__ = f"{name} encoder (reference u2pl/models/resnet.py); pretrained defaults to {pretrained_default}."
+    return build
 
 
-def resnet34(pretrained=False, **kwargs):
-    return _build("resnet34", BasicBlock, [3, 4, 6, 3], pretrained, **kwargs)
-
-
-def resnet50(pretrained=True, **kwargs):
-    return _build("resnet50", Bottleneck, [3, 4, 6, 3], pretrained, **kwargs)
-
-
-def resnet101(pretrained=True, **kwargs):
-    return _build("resnet101", Bottleneck, [3, 4, 23, 3], pretrained, **kwargs)
-
-
-def resnet152(pretrained=True, **kwargs):
-    return _build("resnet152", Bottleneck, [3, 8, 36, 3], pretrained, **kwargs)
+resnet18, resnet34, resnet50, resnet101, resnet152 = (_factory(n) for n in _ARCHS)
+__all__ = ["ResNet"] + list(_ARCHS)

@@ -1,4 +1,5 @@
-"""Drop-in for u2pl/utils/dist_helper.py:13-46: one process per GPU, NCCL over NVLink."""
+"""`setup_distributed` for the drop-in `u2pl.utils.dist_helper` (reference :13-46): one process per GPU,
+rank / world size from SLURM or from the torchrun environment, NCCL process group over NVLink."""
 import os
 import subprocess
 
@@ -6,22 +7,24 @@ import torch
 import torch.distributed as dist
 
 
+def _slurm_env(port):
+    """Translate SLURM variables into the env:// rendezvous torch.distributed expects."""
+    env = os.environ
+    rank, world = int(env["SLURM_PROCID"]), int(env["SLURM_NTASKS"])
+    head = subprocess.getoutput(f"scontrol show hostname {env['SLURM_NODELIST']} | head -n1")
+    if port is not None:
+        env["MASTER_PORT"] = str(port)
+    env.setdefault("MASTER_PORT", "10685")
+    env.setdefault("MASTER_ADDR", head)
+    env.update(WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(rank % torch.cuda.device_count()))
+    return rank, world
+
+
 def setup_distributed(backend="nccl", port=None):
-    num_gpus = torch.cuda.device_count()
     if "SLURM_JOB_ID" in os.environ:
-        rank = int(os.environ["SLURM_PROCID"])
-        world_size = int(os.environ["SLURM_NTASKS"])
-        addr = subprocess.getoutput(f"scontrol show hostname {os.environ['SLURM_NODELIST']} | head -n1")
-        if port is not None:
-            os.environ["MASTER_PORT"] = str(port)
-        os.environ.setdefault("MASTER_PORT", "10685")
-        os.environ.setdefault("MASTER_ADDR", addr)
-        os.environ["WORLD_SIZE"] = str(world_size)
-        os.environ["LOCAL_RANK"] = str(rank % num_gpus)
-        os.environ["RANK"] = str(rank)
+        rank, world = _slurm_env(port)
     else:
-        rank = int(os.environ["RANK"])
-        world_size = int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(rank % num_gpus)
-    dist.init_process_group(backend=backend, world_size=world_size, rank=rank)
-    return rank, world_size
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(rank % torch.cuda.device_count())
+    dist.init_process_group(backend=backend, world_size=world, rank=rank)
+    return rank, world
