@@ -65,11 +65,15 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
+    if build_if_missing:
+        try:
+            _build.build()                     # no-op when the source digest matches the stamp; rebuilds a stale library
+        except RuntimeError:
+            if not os.path.exists(LIB_PATH):
+                raise
     if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise U2PLNativeError(f"{LIB_PATH} is missing; run `python -m u2pl_b200.build`")
-        from . import build as _build
-        _build.build()
+        raise U2PLNativeError(f"{LIB_PATH} is missing; run `python -m u2pl_b200.build` (there is no fallback path)")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library drift: fail loudly
