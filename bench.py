@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- train-step images/sec of the U2PL semi-supervised step (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload v16|c2|tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|eager] [--workload v16|c2|tiny]
 
 Workload at N=1: BASELINE.json configs[1] -- train_semi.py U2PL VOC, ResNet101-DeepLabv3+,
 513x513 crops, C=21, batch 16 labelled + 16 unlabelled, mid-training epoch (40/80) so that
@@ -16,6 +16,10 @@ masked CE, contrastive memory-bank loss, backward, SGD, EMA.
 fp32 network + oracle losses) on the host cores, on a bounded sample (1 labelled + 1 unlabelled
 crop per step).  The reference itself is Python and cannot travel to the GPU box (/root/reference
 does not exist there); the oracle is pinned to it by tests/golden.
+
+`--impl eager` (one GPU) times oracle/eager_step.py: the same step with the reference's own device placement
+(torch-eager fp32 network and per-pixel math on the GPU, numpy percentiles and memory banks on the host) --
+the "reference PyTorch-eager step" BASELINE.json's north_star compares against.
 """
 import argparse
 import json
@@ -185,6 +189,81 @@ def print_reference(args):
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# =========================================================================== torch-eager comparator (GPU)
+def eager_arm(args, dev=None):
+    """the reference step as the reference runs it on a GPU -- torch-eager fp32 (cuDNN TF32
+    allowed, torch's default), host percentiles, CPU banks, per-class Python loops -- via oracle/eager_step.py.
+    Single GPU only (rank 0); halves the batch on a CUDA OOM and says so in `config`."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import eager_step, model_port
+    arch, C, crop, bl, bu, _, aux = WORKLOADS[args.workload]
+    if dev is None:                                           # `dev="cpu"` is for the plumbing test only
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl eager needs a CUDA device (use --impl reference for the CPU arm)")
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.cuda.set_device(dev)
+        torch.backends.cudnn.benchmark = True
+    dev = torch.device(dev)
+    on_gpu = dev.type == "cuda"
+    cfg = make_cfg(args.workload)
+    base = model_port.init_state(arch, C, aux, seed=1, peak=PEAK)
+
+    def on_dev():
+        return {k: v.detach().to(dev).requires_grad_(v.requires_grad) for k, v in base.items()}
+
+    while True:
+        try:
+            ref = eager_step.EagerStep(on_dev(), on_dev(), cfg, arch)
+            g = torch.Generator().manual_seed(7)
+            for c in range(C):                                # banks pre-filled to capacity, on the host as in the reference
+                ref.memobank[c][0] = torch.randn(ref.queue_size[c], 256, generator=g)
+            image_l, label_l, image_u = synth_batch(1234, bl, bu, crop, C)
+            np.random.seed(1234)
+            torch.manual_seed(1234)
+            it = EPOCH * LEN_LOADER
+            for _ in range(max(args.warmup, 3) if on_gpu else args.warmup):
+                ref.step(image_l, label_l, image_u, EPOCH, it, LEN_LOADER)
+                it += 1
+            clocks = ClockSampler(dev.index or 0)
+            if on_gpu:
+                clocks.start()
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                losses = ref.step(image_l, label_l, image_u, EPOCH, it, LEN_LOADER)
+                it += 1
+            if on_gpu:
+                e.record()
+                torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            ms = s.elapsed_time(e) / args.steps if on_gpu else wall_ms
+            clk = clocks.stop() if on_gpu else None
+            break
+        except torch.cuda.OutOfMemoryError:
+            if bl == 1:
+                raise
+            del ref
+            torch.cuda.empty_cache()
+            bl, bu = bl // 2, bu // 2
+    value = (bl + bu) / (ms * 1e-3)
+    h2d = image_l.numel() * 4 + label_l.numel() * 8 + image_u.numel() * 4
+    line = {
+        "impl": "eager", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "wall_ms_per_step": wall_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cuDNN TF32 allowed: torch default)", "data": "synthetic",
+        "config": {"workload": f"train_semi.py U2PL step as the reference executes it (oracle/eager_step.py), {arch}-DeepLabv3+ "
+                               f"{crop}x{crop} C={C}, {bl}+{bu} crops, epoch {EPOCH}/80, CPU banks full (30k/50k x 256)",
+                   "global_batch": bl + bu, "requested_batch": WORKLOADS[args.workload][3] * 2, "l2": "inputs_exceed_L2"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                "note": "host inputs are copied inside every step (train_semi.py:283,287), so value == e2e"},
+        "gpu_launches": 0, "clocks": clk, "losses": [float(x) for x in losses]}
+    print(json.dumps(line))
+    return line
 
 
 # =========================================================================== our arm (GPU)
@@ -364,13 +443,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--workload", default="v16", choices=sorted(WORKLOADS))
     ap.add_argument("--fp32", action="store_true", help="network in fp32 (TF32 off) instead of bf16 autocast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         print_reference(args)
+    elif args.impl == "eager":
+        eager_arm(args)
     else:
         our_arm(args)
 

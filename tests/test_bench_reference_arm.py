@@ -26,3 +26,16 @@ def test_usable_cores_respects_cgroup_quota(tmp_path, monkeypatch):
     import bench
     n = bench.usable_cores()
     assert 1 <= n <= (os.cpu_count() or 1)
+
+
+def test_eager_arm_plumbing_on_cpu(capsys):
+    """`--impl eager` needs a GPU; its code path (state on device, host banks at capacity, timing, JSON line) is
+    exercised here on the CPU device with the tiny workload."""
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    args = argparse.Namespace(workload="tiny", steps=1, warmup=0, gpus=1)
+    line = bench.eager_arm(args, dev="cpu")
+    assert line["impl"] == "eager" and line["value"] > 0 and line["config"]["global_batch"] == 4
+    assert len(line["losses"]) == 3 and line["losses"][2] > 0            # contrastive branch ran against full banks
+    assert json.loads(capsys.readouterr().out.strip().splitlines()[-1])["impl"] == "eager"
