@@ -252,6 +252,21 @@ int u2pl_bn_backward_elemt(const void *dy, const void *x, const void *y, const f
 int u2pl_gemm_bf16_tn(const void *A, const void *B, void *D, int64_t M, int64_t N, int64_t K,
                       const float *scale, const float *shift, int relu, void *stream);
 
+/* ------------------------------------------------------------------------
+ * A1  stride-1 "same" convolution as an implicit GEMM on the tensor cores (tcgen05 + 4-D TMA boxes, no im2col),
+ *     epilogue = folded eval-mode BatchNorm scale/shift, residual add, ReLU
+ * replaces: conv3x3 / conv1x1 (resnet.py:25-41) + BatchNorm (eval) + `out += identity` + ReLU (resnet.py:118-140),
+ *           the dilated ASPP branches (base.py:38-75) and the decoder heads' convs (decoder.py:60-113) on the
+ *           teacher's pseudo-label forward (train_semi.py:318-319).
+ *   x [n,h,w,cin], out / residual [n,h,w,cout] bf16 channels-last dense; wgt [cout, ksize, ksize, cin] bf16 (the
+ *   memory of a channels-last weight tensor); padding = dilation * (ksize / 2); ksize 1 or 3; fp32 accumulation;
+ *   out = act((conv) * scale[co] + shift[co] + residual); scale/shift/residual may be NULL.  cin % 8 == 0,
+ *   cout % 8 == 0, pointers 16-byte aligned.
+ * ---------------------------------------------------------------------- */
+int u2pl_conv_bf16_nhwc(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w, int64_t cin,
+                        int64_t cout, int ksize, int dilation, const float *scale, const float *shift,
+                        const void *residual, int relu, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,86 @@
+"""GPU: tcgen05 implicit-GEMM convolution (csrc/conv_tc.cu, `u2pl_conv_bf16_nhwc`) against F.conv2d in fp32 on the
+same bf16-representable inputs; tolerance = bf16 rounding of the output (1e-2 relative to the output scale).
+
+OPT-IN (U2PL_TC_CONV=1): this kernel was written after round 1's GPU minutes were spent and has not executed on a
+B200 yet, so it is neither on the default path (fused.ENABLED["tc_conv"]) nor in the default GPU suite.  First GPU
+call of the next round: `U2PL_TC_CONV=1 python -m pytest tests/test_gpu_conv_tc.py -x -q`."""
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("U2PL_TC_CONV", "0") != "1", reason="unvalidated kernel: set U2PL_TC_CONV=1")]
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+CASES = [  # N, Cin, H, W, Cout, k, dilation, affine, residual, relu
+    (2, 64, 33, 31, 128, 3, 1, True, False, True),        # stem-like, odd sizes, partial pixel tiles
+    (2, 256, 65, 65, 256, 3, 2, True, False, True),       # layer3 conv2
+    (1, 512, 65, 65, 512, 3, 16, True, False, True),      # layer4 multi-grid d=16
+    (2, 2048, 65, 65, 256, 3, 12, True, False, True),     # ASPP d=12
+    (1, 2048, 65, 65, 256, 3, 36, False, False, False),   # ASPP d=36, raw product
+    (2, 256, 65, 65, 1024, 1, 1, True, True, True),       # bottleneck conv3 + residual + ReLU
+    (3, 1024, 17, 19, 256, 1, 1, True, False, True),      # conv1, M not a multiple of 128
+    (16, 2048, 1, 1, 256, 1, 1, True, False, True),       # ASPP pooled branch (1x1 map)
+    (1, 72, 20, 24, 40, 3, 3, True, True, False),         # Cin % 64 != 0 (tap boundary inside a K block), partial N tile
+    (2, 304, 129, 129, 256, 3, 1, False, False, True),    # decoder-like, 129x129
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_matches_torch(case):
+    from u2pl_b200 import ops
+    N, Cin, H, W, Cout, k, d, affine, res, relu = case
+    torch.manual_seed(Cin + Cout + d)
+    x = _cl((torch.randn(N, Cin, H, W, device="cuda")).bfloat16())
+    w = _cl((torch.randn(Cout, Cin, k, k, device="cuda") / (Cin * k * k) ** 0.5).bfloat16())
+    scale = torch.rand(Cout, device="cuda") + 0.5 if affine else None
+    shift = torch.randn(Cout, device="cuda") if affine else None
+    r = _cl(torch.randn(N, Cout, H, W, device="cuda").bfloat16()) if res else None
+    got = ops.conv_bf16_nhwc(x, w, d, scale, shift, r, relu)
+    assert got.shape == (N, Cout, H, W) and got.is_contiguous(memory_format=torch.channels_last)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(x.float(), w.float(), None, 1, d * (k // 2), d)
+    if affine:
+        ref = ref * scale[None, :, None, None] + shift[None, :, None, None]
+    if res:
+        ref = ref + r.float()
+    if relu:
+        ref = F.relu(ref)
+    err = (got.float() - ref).abs().max().item()
+    assert err <= 1e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_eval_model_same_with_and_without_tc_conv():
+    import copy
+    import u2pl_b200
+    from u2pl_b200 import fused
+    u2pl_b200.install()
+    from u2pl.models.model_helper import ModelBuilder
+    net = {"num_classes": 21, "sync_bn": False, "ema_decay": 0.99,
+           "encoder": {"type": "u2pl.models.resnet.resnet50",
+                       "kwargs": {"multi_grid": True, "zero_init_residual": False, "fpn": True,
+                                  "replace_stride_with_dilation": [False, True, True], "pretrained": False}},
+           "decoder": {"type": "u2pl.models.decoder.dec_deeplabv3_plus", "kwargs": {"inner_planes": 256, "dilations": [12, 24, 36]}}}
+    torch.manual_seed(0)
+    m = ModelBuilder(copy.deepcopy(net)).cuda().to(memory_format=torch.channels_last).eval()
+    for mod in m.modules():                                    # non-trivial running statistics
+        if isinstance(mod, nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+    x = _cl(torch.randn(2, 3, 129, 129, device="cuda"))
+    outs = {}
+    for flag in (False, True):
+        fused.ENABLED["tc_conv"] = flag
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            outs[flag] = {k: v.float() for k, v in m(x).items()}
+    fused.ENABLED["tc_conv"] = True
+    for k in ("pred", "rep"):
+        a, b = outs[False][k], outs[True][k]
+        assert (a - b).norm() <= 0.03 * a.norm(), (k, float((a - b).norm() / a.norm()))

@@ -1,0 +1,281 @@
+// conv_tc.cu -- stride-1 "same" convolution (1x1, or RxS with dilation) of a channels-last bf16 tensor as an
+// IMPLICIT GEMM on the tcgen05 tensor cores, with the eval-mode BatchNorm scale/shift, the residual add and
+// the ReLU of a ResNet block folded into the epilogue:
+//
+//     out[n,h,w,co] = act( (sum_{r,s,ci} x[n, h+(r-R/2)d, w+(s-S/2)d, ci] * wgt[co,r,s,ci]) * scale[co] + shift[co]
+//                          + residual[n,h,w,co] )
+//
+// It is the contraction behind every stride-1 convolution of the network (resnet.py:25-41 conv3x3/conv1x1,
+// base.py:38-75 ASPP branches d=12/24/36, decoder.py:60-113 heads), used for the teacher's eval-mode
+// pseudo-label forward (train_semi.py:318-319).
+//
+// No im2col buffer exists anywhere: the A operand of tap (r,s), channel block kb, is ONE 4-D TMA box
+// {64 channels, TW, TH, 1 image} of x fetched at spatial offset ((r-R/2)d, (s-S/2)d) -- TMA zero-fills the
+// part of the box that falls outside the image (negative or >= H/W coordinates), which is exactly the zero
+// padding of the convolution -- and lands in shared memory as the same 128-row x 128-byte SWIZZLE_128B K-major
+// tile the flat GEMM uses (row = i*TW + j).  The weights are read as the row-major [Cout, R*S*Cin] matrix a
+// channels-last weight tensor already is.  All taps and channel blocks accumulate into one TMEM tile.
+// A 1x1 convolution uses the same kernel with the tensor viewed as {Cin, N*H*W, 1, 1} and a {64,128,1,1} box
+// (no spatial tiling, no tile waste).
+//
+// CTA layout, pipeline and barriers are those of gemm_bf16_tn_persistent_kernel (gemm_tc.cu): warp 0 TMA
+// producer, warp 1 TMEM allocation + single-thread MMA issue, warps 2-5 epilogue, 4-stage smem ring, two
+// TMEM accumulator stages, one persistent CTA per SM looping over (pixel tile, channel tile) pairs.
+#include <cstdlib>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace u2pl {
+
+namespace convtc {
+constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 4;
+constexpr int kTileABytes = kBM * kBK * 2, kTileBBytes = kBN * kBK * 2;
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 128;
+}  // namespace convtc
+
+struct ConvParams {
+    int Nimg, H, W, Cin, Cout;        // logical NHWC geometry the tensor map was built from (flat 1x1: Nimg=H=1, W=N*H*W)
+    int R, S, dil;                    // taps and dilation (R, S odd)
+    int log2_tw;                      // pixel tile = TH x TW with TH*TW == 128, TW = 1 << log2_tw
+    int tiles_h, tiles_w;             // pixel tiles per image
+    const float *scale, *shift;       // [Cout] or null
+    const __nv_bfloat16 *residual;    // same layout as D, or null
+    int relu;
+    __nv_bfloat16 *D;
+};
+
+__global__ void __launch_bounds__(convtc::kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, ConvParams p)
+{
+    using namespace convtc;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t *sA = smem, *sB = smem + kStages * kTileABytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sB + kStages * kTileBBytes);
+    uint64_t *empty = full + kStages;
+    uint64_t *tmem_full = empty + kStages;            // [2]
+    uint64_t *tmem_empty = tmem_full + 2;             // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *s_par = reinterpret_cast<float *>(tmem_slot + 2);      // [2 stages][scale 128 | shift 128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tw = 1 << p.log2_tw, th = kBM >> p.log2_tw;
+    const int tiles_img = p.tiles_h * p.tiles_w;
+    const int tiles_m = p.Nimg * tiles_img, tiles_n = (p.Cout + kBN - 1) / kBN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int kb_per_tap = (p.Cin + kBK - 1) / kBK;
+    const int nkb = p.R * p.S * kb_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                              // ---------------- TMA producer
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int tm = t / tiles_n, n0 = (t % tiles_n) * kBN;
+                const int img = tm / tiles_img, rem = tm % tiles_img;
+                const int h0 = (rem / p.tiles_w) * th, w0 = (rem % p.tiles_w) * tw;
+                for (int tap = 0; tap < p.R * p.S; ++tap) {
+                    const int dh = (tap / p.S - p.R / 2) * p.dil, dw = (tap % p.S - p.S / 2) * p.dil;
+                    for (int kb = 0; kb < kb_per_tap; ++kb, ++it) {
+                        const int s = it % kStages;
+                        mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
+                        mbar_expect_tx(full + s, kTileABytes + kTileBBytes);
+                        tma_load_4d(sA + s * kTileABytes, &map_x, full + s, kb * kBK, w0 + dw, h0 + dh, img);
+                        // weight columns of this tap start at tap*Cin; when Cin % 64 != 0 the last block of a tap also
+                        // fetches the first columns of the next tap, which meet zero-filled A channels (product 0)
+                        tma_load_2d(sB + s * kTileBBytes, &map_w, full + s, tap * p.Cin + kb * kBK, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                              // ---------------- MMA issuer
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kBN >> 3) << 17) |
+                                   (static_cast<uint32_t>(kBM >> 4) << 24);
+            uint32_t it = 0, tile_i = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_i) {
+                const uint32_t acc = tile_i & 1, use = tile_i >> 1;
+                mbar_wait(tmem_empty + acc, (use & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + acc * kTmemCols;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(full + s, (it / kStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = smem_u32(sA + s * kTileABytes), b0 = smem_u32(sB + s * kTileBBytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        umma_f16(d_tmem, smem_desc_sw128(a0 + 32 * k), smem_desc_sw128(b0 + 32 * k), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(empty + s);
+                }
+                umma_commit(tmem_full + acc);
+            }
+        }
+    } else {                                          // ---------------- epilogue (warps 2..5)
+        const int q = warp & 3;
+        const bool affine = p.scale != nullptr || p.shift != nullptr;
+        const int m = q * 32 + lane, ti = m >> p.log2_tw, tj = m & (tw - 1);
+        uint32_t tile_i = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_i) {
+            const int tm = t / tiles_n, n0 = (t % tiles_n) * kBN;
+            const int img = tm / tiles_img, rem = tm % tiles_img;
+            const int h = (rem / p.tiles_w) * th + ti, w = (rem % p.tiles_w) * tw + tj;
+            const bool live = h < p.H && w < p.W;
+            const size_t pix = (static_cast<size_t>(img) * p.H + h) * p.W + w;
+            const uint32_t acc = tile_i & 1, use = tile_i >> 1;
+            float *s_scale = s_par + acc * 2 * kBN, *s_shift = s_scale + kBN;
+            if (affine) {
+                const int e = threadIdx.x - 64, c = n0 + e;
+                s_scale[e] = (p.scale && c < p.Cout) ? __ldg(p.scale + c) : 1.0f;
+                s_shift[e] = (p.shift && c < p.Cout) ? __ldg(p.shift + c) : 0.0f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            mbar_wait(tmem_full + acc, use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int j = 0; j < kBN / 32; ++j) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + acc * kTmemCols + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(j * 32), r);
+                if (j == kBN / 32 - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty + acc);
+                }
+                const int c0 = n0 + j * 32;
+                if (live) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int c = c0 + g * 8;
+                        if (c < p.Cout) {             // Cout % 8 == 0
+                            const size_t off = pix * p.Cout + c;
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                v[e] = __uint_as_float(r[g * 8 + e]);
+                                if (affine) v[e] = fmaf(v[e], s_scale[j * 32 + g * 8 + e], s_shift[j * 32 + g * 8 + e]);
+                            }
+                            if (p.residual) {
+                                const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(p.residual + off));
+                                const __nv_bfloat162 *rh = reinterpret_cast<const __nv_bfloat162 *>(&rr);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = __bfloat1622float2(rh[e]);
+                                    v[2 * e] += f.x;
+                                    v[2 * e + 1] += f.y;
+                                }
+                            }
+                            if (p.relu) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
+                            }
+                            uint4 o;
+                            __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                            *reinterpret_cast<uint4 *>(p.D + off) = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kTmemCols) : "memory");
+}
+
+// x viewed as {C, W, H, N} (innermost first), bf16, dense NHWC; box {64, tw, th, 1}; 128-byte swizzle; zero OOB fill
+static bool make_map_nhwc(CUtensorMap *map, const void *base, int64_t n, int64_t h, int64_t w, int64_t c, int th, int tw)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2, static_cast<cuuint64_t>(h) * w * c * 2};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(convtc::kBK), static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool make_map_weight(CUtensorMap *map, const void *base, int64_t cout, int64_t ktot)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(cout)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(convtc::kBK), static_cast<cuuint32_t>(convtc::kBN)};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace u2pl
+
+using namespace u2pl;
+
+extern "C" int u2pl_conv_bf16_nhwc(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w, int64_t cin,
+                                   int64_t cout, int ksize, int dilation, const float *scale, const float *shift,
+                                   const void *residual, int relu, void *stream)
+{
+    using namespace convtc;
+    if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || (cin % 8) || (cout % 8) || (ksize != 1 && ksize != 3) || dilation < 1)
+        return bad_arg("conv_bf16_nhwc: need Cin % 8 == 0, Cout % 8 == 0, ksize in {1,3}, dilation >= 1");
+    if (n * h * w >= (1LL << 31) || static_cast<int64_t>(ksize) * ksize * cin >= (1LL << 31))
+        return bad_arg("conv_bf16_nhwc: tensor too large for 32-bit TMA coordinates");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(out) |
+         reinterpret_cast<uintptr_t>(residual)) & 15)
+        return bad_arg("conv_bf16_nhwc: operands must be 16-byte aligned");
+    ConvParams p;
+    CUtensorMap mx, mw;
+    bool ok;
+    if (ksize == 1) {                                 // flat: every 128 consecutive pixels are one tile
+        p.Nimg = 1; p.H = 1; p.W = static_cast<int>(n * h * w);
+        p.log2_tw = 7; p.tiles_h = 1; p.tiles_w = (p.W + kBM - 1) / kBM;
+        ok = make_map_nhwc(&mx, x, 1, 1, n * h * w, cin, 1, kBM);
+    } else {                                          // 8 x 16 pixel tiles inside each image
+        p.Nimg = static_cast<int>(n); p.H = static_cast<int>(h); p.W = static_cast<int>(w);
+        p.log2_tw = 4; p.tiles_h = (p.H + 7) / 8; p.tiles_w = (p.W + 15) / 16;
+        ok = make_map_nhwc(&mx, x, n, h, w, cin, 8, 16);
+    }
+    ok = ok && make_map_weight(&mw, wgt, cout, static_cast<int64_t>(ksize) * ksize * cin);
+    if (!ok) { set_error("conv_bf16_nhwc: cuTensorMapEncodeTiled failed"); return U2PL_E_BADARG; }
+    p.Cin = static_cast<int>(cin); p.Cout = static_cast<int>(cout);
+    p.R = p.S = ksize; p.dil = dilation;
+    p.scale = scale; p.shift = shift; p.residual = static_cast<const __nv_bfloat16 *>(residual); p.relu = relu;
+    p.D = static_cast<__nv_bfloat16 *>(out);
+    const size_t smem = static_cast<size_t>(kStages) * (kTileABytes + kTileBBytes) + 1024 + 256 + 4 * kBN * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
+        configured = true;
+    }
+    const long long tiles = static_cast<long long>(p.Nimg) * p.tiles_h * p.tiles_w * ((cout + kBN - 1) / kBN);
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned g = static_cast<unsigned>(tiles < sms ? tiles : sms);
+    conv_tc_kernel<<<g, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(mx, mw, p);
+    return check_launch("conv_bf16_nhwc");
+}

@@ -24,7 +24,11 @@ import torch.nn.functional as F
 from . import _lib
 from .ops import _p, _stream
 
-ENABLED = {"bn": True, "wgrad": True}
+import os
+
+# "tc_conv": eval-mode conv + BN (+residual, +ReLU) through the tcgen05 implicit-GEMM kernel (csrc/conv_tc.cu).
+# Off unless U2PL_TC_CONV=1: the kernel was written after round 1's GPU minutes were spent and has not run on a B200 yet.
+ENABLED = {"bn": True, "wgrad": True, "tc_conv": os.environ.get("U2PL_TC_CONV", "0") == "1"}
 
 
 def _world():
@@ -119,12 +123,44 @@ def bn_act(x, bn, relu=None, residual=None):
     return relu(y) if isinstance(relu, nn.Module) else F.relu(y)
 
 
+def _tc_conv_ok(x, conv, bn, residual):
+    k, d = conv.kernel_size[0], conv.dilation[0]
+    return (ENABLED["tc_conv"] and not bn.training and not torch.is_grad_enabled() and _is_cl_bf16(x)
+            and isinstance(conv, nn.Conv2d) and isinstance(bn, (nn.BatchNorm2d, nn.SyncBatchNorm))
+            and conv.kernel_size in ((1, 1), (3, 3)) and conv.stride == (1, 1) and conv.dilation == (d, d)
+            and conv.padding == (d * (k // 2), d * (k // 2)) and conv.groups == 1 and conv.bias is None
+            and conv.padding_mode == "zeros" and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0
+            and bn.track_running_stats and (residual is None or _is_cl_bf16(residual)))
+
+
+def conv_bn_act(x, conv, bn, relu=None, residual=None):
+    """relu(bn(conv(x)) + residual).  Eval mode without autograd (the teacher's pseudo-label forward) on channels-last
+    bf16 activations: ONE implicit-GEMM kernel with the folded BatchNorm, the residual and the ReLU in its epilogue;
+    otherwise the convolution module followed by `bn_act`."""
+    if not _tc_conv_ok(x, conv, bn, residual):
+        return bn_act(conv(x), bn, relu, residual)
+    from .ops import conv_bf16_nhwc
+    lib = _lib.load()
+    C = conv.out_channels
+    scale = torch.empty(C, dtype=torch.float32, device=x.device)
+    shift = torch.empty(C, dtype=torch.float32, device=x.device)
+    _lib.check(lib.u2pl_bn_fold(C, _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), float(bn.eps),
+                                _p(scale), _p(shift), _stream()), "u2pl_bn_fold")
+    return conv_bf16_nhwc(x, conv.weight, conv.dilation[0], scale, shift, residual, relu is not None and relu is not False)
+
+
 def run_sequential(seq, x):
-    """nn.Sequential.forward with (norm, ReLU) pairs fused."""
+    """nn.Sequential.forward with (conv, norm[, ReLU]) and (norm, ReLU) groups fused."""
     mods = list(seq)
     i = 0
     while i < len(mods):
         m = mods[i]
+        if isinstance(m, nn.Conv2d) and i + 1 < len(mods) and isinstance(mods[i + 1], (nn.BatchNorm2d, nn.SyncBatchNorm)) \
+                and _tc_conv_ok(x, m, mods[i + 1], None):
+            nxt = mods[i + 2] if i + 2 < len(mods) else None
+            x = conv_bn_act(x, m, mods[i + 1], nxt if isinstance(nxt, nn.ReLU) else None)
+            i += 3 if isinstance(nxt, nn.ReLU) else 2
+            continue
         if isinstance(m, (nn.BatchNorm2d, nn.SyncBatchNorm)):
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             if isinstance(nxt, nn.ReLU):

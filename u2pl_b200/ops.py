@@ -281,3 +281,24 @@ def conv1x1_bn_relu_eval(x, weight, scale, shift, relu=True):
     w = weight.reshape(weight.shape[0], Cin).to(torch.bfloat16).contiguous()
     d = gemm_bf16_tn(a, w, scale, shift, relu)
     return d.view(N, H, W, -1).permute(0, 3, 1, 2)               # channels-last view of [N,Cout,H,W]
+
+
+def conv_bf16_nhwc(x, weight, dilation=1, scale=None, shift=None, residual=None, relu=False):
+    """Stride-1 "same" convolution (1x1 or 3x3, padding = dilation * (k // 2)) of a channels-last bf16 activation
+    [N,Cin,H,W] as an implicit GEMM on the tensor cores, epilogue act(conv * scale + shift + residual)
+    (csrc/conv_tc.cu).  `weight` [Cout,Cin,k,k] in any layout/dtype (a channels-last bf16 weight is used in place)."""
+    _need_cuda(x, weight, scale, shift, residual)
+    lib = _lib.load()
+    N, Cin, H, W = x.shape
+    Cout, k = weight.shape[0], weight.shape[2]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    assert weight.shape[1] == Cin and weight.shape[3] == k and k in (1, 3)
+    wk = weight.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()           # [Cout,k,k,Cin]; no copy when channels-last
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape == (N, Cout, H, W) \
+            and residual.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty((N, Cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    rc = lib.u2pl_conv_bf16_nhwc(_p(x), _p(wk), _p(out), N, H, W, Cin, Cout, k, int(dilation), _p(scale), _p(shift),
+                                 _p(residual), int(bool(relu)), _stream())
+    _lib.check(rc, "u2pl_conv_bf16_nhwc")
+    return out

@@ -10,7 +10,7 @@ classes per variant, and the forward passes go through the fused BN(+ReLU+residu
 import torch
 import torch.nn as nn
 
-from u2pl_b200.fused import DilatedConv2d, StemConv2d, bn_act, run_sequential
+from u2pl_b200.fused import DilatedConv2d, StemConv2d, bn_act, conv_bn_act, run_sequential
 
 from .base import _norm
 
@@ -70,9 +70,9 @@ class _Residual(nn.Module):
         shortcut = x if self.downsample is None else run_sequential(self.downsample, x)
         y = x
         for i in range(1, self._depth):
-            y = bn_act(getattr(self, f"conv{i}")(y), getattr(self, f"bn{i}"), self.relu)
+            y = conv_bn_act(y, getattr(self, f"conv{i}"), getattr(self, f"bn{i}"), self.relu)
         last = self._depth
-        return bn_act(getattr(self, f"conv{last}")(y), getattr(self, f"bn{last}"), self.relu, residual=shortcut)
+        return conv_bn_act(y, getattr(self, f"conv{last}"), getattr(self, f"bn{last}"), self.relu, residual=shortcut)
 
 
 class BasicBlock(_Residual):
