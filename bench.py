@@ -427,7 +427,10 @@ def our_arm(args):
                        "global_batch": imgs, "parallelism": f"dp{world}", "l2": "inputs_exceed_L2",
                        "network": "channels-last bf16 autocast: convs via cuDNN/cuBLAS (library), BN+ReLU+residual and all "
                                   "losses via libu2pl_b200.so",
-                       "classifier_peak_scale": PEAK},
+                       "classifier_peak_scale": PEAK,
+                       "bank": "class-sharded, peer-mapped (U2PL_BANK_SHARDED=1)"
+                               if world > 1 and os.environ.get("U2PL_BANK_SHARDED", "0") == "1" else "replicated per GPU",
+                       "tc_conv_T1": os.environ.get("U2PL_TC_CONV", "0") == "1"},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": 12 * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "tensor_roofline": tensor,

@@ -207,6 +207,28 @@ int u2pl_infonce_forward(const float *rep, int64_t sn, int64_t sd, int64_t sp,
                          int nact, int nq, int nneg, float temperature, int valid_seg,
                          float *loss_q, float *grad_rows, int32_t *anchor_pix, float *loss, void *stream);
 
+/* Same loss with the bank SHARDED BY CLASS across the GPUs of one box (owner(c) = c mod world): the
+ * negatives of an active class are read by the loss kernel itself straight from the owner's shard -- local memory or
+ * a peer GPU's memory mapped with u2pl_shard_open, i.e. 1 KB row loads over NVLink -- instead of being gathered,
+ * exchanged and re-read.  class_bank: DEVICE array [nact] of shard base pointers (one per active class);
+ * neg_rows: rows inside that shard.  Everything else as u2pl_infonce_forward.
+ * replaces: `negative_feat = memobank[valid_classes[i]][0].clone().cuda()` + index (loss_helper.py:192-200). */
+int u2pl_infonce_forward_sharded(const float *rep, int64_t sn, int64_t sd, int64_t sp,
+                                 int64_t P, int64_t D, int64_t hw,
+                                 const uint32_t *an_bits, const uint32_t *blockoff_an,
+                                 const int32_t *act_class, const int32_t *a_ord, const int32_t *neg_rows,
+                                 const float *proto, const float *const *class_bank,
+                                 int nact, int nq, int nneg, float temperature, int valid_seg,
+                                 float *loss_q, float *grad_rows, int32_t *anchor_pix, float *loss, void *stream);
+
+/* Bank shards that peers can map (CUDA IPC; same box, NVLink).  u2pl_shard_alloc: cudaMalloc + zero + export a
+ * 64-byte handle; u2pl_shard_open: map a peer's shard from its handle; u2pl_shard_close: cudaFree (owned != 0) or
+ * unmap.  The handles are exchanged by the host (u2pl_b200/bank.py, one all_gather_object at start-up).
+ * replaces: train_semi.py:161-169 (bank construction) for world size > 1. */
+int u2pl_shard_alloc(int64_t bytes, void **dptr, unsigned char *handle64);
+int u2pl_shard_open(const unsigned char *handle64, void **dptr);
+int u2pl_shard_close(void *dptr, int owned);
+
 /* grad_rep[anchor pixel, :] += upstream * grad_rows (atomics: queries are sampled with replacement). */
 int u2pl_infonce_backward(const float *grad_rows, const int32_t *anchor_pix, int nrows,
                           int64_t D, int64_t hw, int64_t sn, int64_t sd, int64_t sp,

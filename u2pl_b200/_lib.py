@@ -42,6 +42,11 @@ SIGNATURES = {
     "u2pl_bank_append": (c_int, [_P, _P, c_int64, _P, c_int, c_int64, _S]),
     "u2pl_infonce_forward": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P,
                                      c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _S]),
+    "u2pl_infonce_forward_sharded": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P,
+                                             c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _S]),
+    "u2pl_shard_alloc": (c_int, [c_int64, _P, _P]),
+    "u2pl_shard_open": (c_int, [_P, _P]),
+    "u2pl_shard_close": (c_int, [_P, c_int]),
     "u2pl_infonce_backward": (c_int, [_P, _P, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _S]),
     "u2pl_gemm_bf16_tn": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int, _S]),
     "u2pl_conv_bf16_nhwc": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, _P, _P, _P, c_int, _S]),

@@ -64,6 +64,18 @@ def physical_rows(ring, logical_idx):
     return (ring.row_base + (ring.start + idx) % ring.cap).astype(np.int32)
 
 
+def shard_layout(queue_size, world):
+    """Class-sharded placement: class c lives on rank c % world.  Returns (owner[c], row_base[c] inside
+    the owner's shard, rows per shard)."""
+    owner, row_base, rows = [], [], [0] * world
+    for c, cap in enumerate(queue_size):
+        r = c % world
+        owner.append(r)
+        row_base.append(rows[r])
+        rows[r] += int(cap)
+    return owner, row_base, rows
+
+
 class DeviceBank:
     """All class banks in one device tensor + per-class Ring state."""
 
@@ -94,3 +106,101 @@ class DeviceBank:
         self.rows[r.row_base:r.row_base + n] = rows[-n:].to(self.rows.device, self.rows.dtype)
         r.start, r.length = 0, n
         r.ptr = r.cap if rows.shape[0] >= r.cap else n % r.cap
+
+
+class _DevicePtrView:
+    """Zero-copy torch view of raw device memory (own cudaMalloc shard or a peer's IPC mapping)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class ShardedBank:
+    """Banks sharded BY CLASS over the GPUs of one box: rank c % world holds class c's ring in a cudaMalloc'd shard
+    that every other rank maps through CUDA IPC.  Ring bookkeeping (host integers) is replicated for all classes --
+    it is a pure function of the all-gathered key counts -- so every rank can draw `torch.randint(len(bank))` and
+    address the rows exactly as the reference does (loss_helper.py:192-197) without asking the owner anything; the
+    InfoNCE kernel then reads the sampled rows directly from the owner's memory over NVLink
+    (u2pl_infonce_forward_sharded).  Appends touch only the owner's shard (1/world of the replicated traffic).
+
+    Ordering between ranks (all on each rank's compute stream):
+      append(step n) -> tiny all_reduce -> peers' loss kernels read          (read-after-write)
+      peers' loss kernels(step n) -> counts all_gather(step n+1) -> append   (write-after-read; contra._prepare)
+    """
+
+    def __init__(self, queue_size, dim, device, rank, world, group=None):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        lib = _lib.load()
+        self.dim, self.rank, self.world, self.group = int(dim), int(rank), int(world), group
+        self.owner, bases, shard_rows = shard_layout(queue_size, world)
+        self.rings = [Ring(cap=int(cap), row_base=b) for cap, b in zip(queue_size, bases)]
+        self.shard_rows = shard_rows
+        nbytes = max(shard_rows[rank], 1) * self.dim * 4
+        ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        _lib.check(lib.u2pl_shard_alloc(nbytes, ctypes.byref(ptr), handle), "u2pl_shard_alloc")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.base = []
+        for r in range(world):
+            if r == rank:
+                self.base.append(int(ptr.value))
+                continue
+            peer = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+            _lib.check(lib.u2pl_shard_open(buf, ctypes.byref(peer)), "u2pl_shard_open")
+            self.base.append(int(peer.value))
+        self.device = device
+        # the local shard as a tensor (what u2pl_bank_append writes; same device, so as_tensor does not copy)
+        self.rows = torch.as_tensor(_DevicePtrView(self.base[rank], (max(shard_rows[rank], 1), self.dim)), device=device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def owns(self, c):
+        return self.owner[c] == self.rank
+
+    def length(self, c):
+        return self.rings[c].length
+
+    def fence(self):
+        """Orders this rank's appends before any peer's subsequent reads (see class docstring)."""
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)
+
+    def class_base(self, c):
+        return self.base[self.owner[c]]
+
+    def materialize(self, c):
+        """Logical-order copy of bank c on this rank's device (debug / tests; a peer's shard is copied over NVLink)."""
+        import torch
+        r, o = self.rings[c], self.owner[c]
+        if o == self.rank:
+            shard = self.rows
+        else:       # torch places a tensor built from a mapped peer pointer on the peer's device: copy the ring's rows over
+            peer = torch.as_tensor(_DevicePtrView(self.base[o], (max(self.shard_rows[o], 1), self.dim)))
+            shard = torch.empty((r.cap, self.dim), dtype=torch.float32, device=self.device)
+            shard.copy_(peer[r.row_base:r.row_base + r.cap])
+            idx = (r.start + torch.arange(r.length, device=self.device)) % r.cap
+            return shard[idx]
+        idx = (r.start + torch.arange(r.length, device=self.device)) % r.cap + r.row_base
+        return shard[idx]
+
+    def load(self, c, rows):
+        """Adopt pre-existing rows: every rank updates the ring state, only the owner stores the rows."""
+        r = self.rings[c]
+        n = min(int(rows.shape[0]), r.cap)
+        if self.owns(c):
+            self.rows[r.row_base:r.row_base + n] = rows[-n:].to(self.rows.device, self.rows.dtype)
+        r.start, r.length = 0, n
+        r.ptr = r.cap if rows.shape[0] >= r.cap else n % r.cap
+
+    def close(self):
+        from . import _lib
+        lib = _lib.load()
+        for r, b in enumerate(self.base):
+            lib.u2pl_shard_close(b, int(r == self.rank))
+        self.base = []

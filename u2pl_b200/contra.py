@@ -16,13 +16,14 @@ replace the reference's C x (barrier + all_gather_object); rank order is preserv
 rank's bank stays identical to the reference's concatenation order (utils.py:21-38).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import _lib
-from .bank import DeviceBank, physical_rows, plan_append
+from .bank import DeviceBank, ShardedBank, physical_rows, plan_append
 from .ops import _need_cuda, _p, _stream
 
 _BANKS = []          # [(memobank list object, DeviceBank)]; identity-keyed like the driver's own lists
@@ -39,7 +40,11 @@ def bank_for(memobank, queue_size, dim, device):
     for obj, bank in _BANKS:
         if obj is memobank:
             return bank
-    bank = DeviceBank(queue_size, dim, device)
+    rank, world = _world()
+    if world > 1 and os.environ.get("U2PL_BANK_SHARDED", "0") == "1":   # opt-in until validated on a multi-GPU box
+        bank = ShardedBank(queue_size, dim, device, rank, world)
+    else:
+        bank = DeviceBank(queue_size, dim, device)
     for c, slot in enumerate(memobank):
         if slot[0].shape[0] > 0:                       # caller pre-filled the CPU bank: adopt it
             bank.load(c, slot[0])
@@ -94,10 +99,12 @@ class _InfoNCE(torch.autograd.Function):
         grad_rows = torch.empty((nact * nq, D), dtype=torch.float32, device=dev)
         anchor_pix = torch.empty(nact * nq, dtype=torch.int32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        rc = lib.u2pl_infonce_forward(_p(rep), sn, sd, sp, N2 * h * w, D, h * w,
+        sharded = "class_bank" in plan
+        fn = lib.u2pl_infonce_forward_sharded if sharded else lib.u2pl_infonce_forward
+        rc = fn(_p(rep), sn, sd, sp, N2 * h * w, D, h * w,
                                       _p(plan["an_bits"]), _p(plan["blockoff_an"]),
                                       _p(plan["act_class"]), _p(plan["a_ord"]), _p(plan["neg_rows"]),
-                                      _p(plan["proto"]), _p(plan["bank_rows"]),
+                                      _p(plan["proto"]), _p(plan["class_bank"] if sharded else plan["bank_rows"]),
                                       nact, nq, nneg, float(plan["temp"]), int(plan["valid_seg"]),
                                       _p(loss_q), _p(grad_rows), _p(anchor_pix), _p(loss), _stream())
         _lib.check(rc, "u2pl_infonce_forward")
@@ -185,14 +192,18 @@ def _prepare(rep, label_bits, prob_l, prob_u, low_mask, high_mask, cfg, memobank
         else:
             gathered = packed
         descs = []
-        for c in range(C):
+        sharded = isinstance(bank, ShardedBank)
+        for c in range(C):                              # ring state advances for every class on every rank ...
             d, _ = plan_append(bank.rings[c], neg_counts[:, c], [r * kmax + class_base[r, c] for r in range(world)])
-            descs.extend(d)
+            if not sharded or bank.owns(c):             # ... the rows are written by the owner only
+                descs.extend(d)
         if descs:
             dd = _to_device_i32("append_desc", np.asarray(descs, dtype=np.int64), dev)
             rc = lib.u2pl_bank_append(_p(gathered), _p(bank.rows), D, _p(dd), len(descs),
                                       int(max(x[4] for x in descs)), _stream())
             _lib.check(rc, "u2pl_bank_append")
+    if isinstance(bank, ShardedBank):
+        bank.fence()                                    # peers may read my shard only after this step's append
     for c in range(C):                                  # keep the driver-visible state coherent
         queue_prtlis[c][0] = bank.rings[c].ptr          # utils.py:45
         n = bank.rings[c].length
@@ -224,6 +235,9 @@ def _prepare(rep, label_bits, prob_l, prob_u, low_mask, high_mask, cfg, memobank
         plan["act_class"] = _to_device_i32("act_class", np.asarray(act), dev)
         plan["a_ord"] = _to_device_i32("a_ord", np.stack(a_ord), dev)
         plan["neg_rows"] = _to_device_i32("neg_rows", np.stack(n_rows), dev)
+        if isinstance(bank, ShardedBank):               # base of the shard holding each active class (maybe a peer's)
+            ptrs = np.asarray([bank.class_base(valid_classes[j]) for j in act], dtype=np.int64)
+            plan["class_bank"] = torch.from_numpy(ptrs).to(dev)
     return plan
 
 

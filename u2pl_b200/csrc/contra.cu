@@ -19,6 +19,7 @@
 // Feature tensors are addressed through element strides (sn, sd, sp) so both NCHW
 // (sd = h*w, sp = 1) and channels-last (sd = 1, sp = D) layouts are read in place.
 #include <algorithm>
+#include <cstring>
 #include "common.cuh"
 
 namespace u2pl {
@@ -395,6 +396,9 @@ struct InfoNceArgs {
     float *loss_q;                  // [nact*nq]  per-query CE
     float *grad_rows;               // [nact*nq][D]  scale * d CE_q / d anchor
     int32_t *anchor_pix;            // [nact*nq]
+    const float *const *class_bank; // kPeer only: [nact] base of the bank shard that holds the active class's ring --
+                                    // local memory or a peer GPU's (CUDA IPC mapping, read over NVLink); neg_rows are
+                                    // rows inside that shard
 };
 
 __device__ __forceinline__ float2 warp_sum2(float a, float b)
@@ -407,6 +411,7 @@ __device__ __forceinline__ float2 warp_sum2(float a, float b)
     return make_float2(a, b);
 }
 
+template <bool kPeer>
 __global__ void __launch_bounds__(128)
 infonce_fwd_kernel(InfoNceArgs a)
 {
@@ -475,6 +480,7 @@ infonce_fwd_kernel(InfoNceArgs a)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { V[j] = 0.0f; K0[j] = 0.0f; }
     const int32_t *rows = a.neg_rows + static_cast<size_t>(w) * a.nneg;
+    const float *bank = kPeer ? a.class_bank[act] : a.bank;
     const bool c0 = d0 < a.D, c1 = d1 < a.D;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float *kr0 = a.proto + static_cast<size_t>(cls) * a.D;
@@ -483,7 +489,7 @@ infonce_fwd_kernel(InfoNceArgs a)
     for (int t = 0; t <= a.nneg; ++t) {
         const float4 x0 = n0, x1 = n1;
         if (t < a.nneg) {
-            const float *kn_ = a.bank + static_cast<size_t>(__ldg(rows + t)) * a.D;
+            const float *kn_ = bank + static_cast<size_t>(__ldg(rows + t)) * a.D;
             n0 = c0 ? __ldg(reinterpret_cast<const float4 *>(kn_ + d0)) : z4;
             n1 = c1 ? __ldg(reinterpret_cast<const float4 *>(kn_ + d1)) : z4;
         }
@@ -685,14 +691,78 @@ extern "C" int u2pl_infonce_forward(const float *rep, int64_t sn, int64_t sd, in
     a.hw = static_cast<uint32_t>(hw); a.P = static_cast<uint32_t>(P); a.D = static_cast<uint32_t>(D);
     a.nb = static_cast<uint32_t>((P + kBlk - 1) / kBlk);
     a.an_bits = an_bits; a.blockoff_an = blockoff_an; a.act_class = act_class; a.a_ord = a_ord; a.neg_rows = neg_rows;
-    a.proto = proto; a.bank = bank; a.nact = nact; a.nq = nq; a.nneg = nneg;
+    a.proto = proto; a.bank = bank; a.class_bank = nullptr; a.nact = nact; a.nq = nq; a.nneg = nneg;
     a.inv_temp = 1.0f / temperature;
     a.scale = 1.0f / (static_cast<float>(nq) * static_cast<float>(valid_seg));
     a.loss_q = loss_q; a.grad_rows = grad_rows; a.anchor_pix = anchor_pix;
     const int warps = nact * nq;
-    infonce_fwd_kernel<<<(warps + 3) / 4, 128, 0, s>>>(a);
+    infonce_fwd_kernel<false><<<(warps + 3) / 4, 128, 0, s>>>(a);
     infonce_loss_kernel<<<1, 256, 0, s>>>(loss_q, warps, a.scale, loss);
     return check_launch("infonce_forward", 2);
+}
+
+extern "C" int u2pl_infonce_forward_sharded(const float *rep, int64_t sn, int64_t sd, int64_t sp,
+                                            int64_t P, int64_t D, int64_t hw,
+                                            const uint32_t *an_bits, const uint32_t *blockoff_an,
+                                            const int32_t *act_class, const int32_t *a_ord, const int32_t *neg_rows,
+                                            const float *proto, const float *const *class_bank,
+                                            int nact, int nq, int nneg, float temperature, int valid_seg,
+                                            float *loss_q, float *grad_rows, int32_t *anchor_pix, float *loss, void *stream)
+{
+    if (D <= 0 || D > kMaxD || D % 4 != 0) return bad_arg("infonce_forward_sharded: D must be a multiple of 4, <= 256");
+    if (nact <= 0 || nq <= 0 || nneg < 0 || valid_seg <= 0) return bad_arg("infonce_forward_sharded: empty problem");
+    if (!class_bank) return bad_arg("infonce_forward_sharded: class_bank is NULL");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    InfoNceArgs a;
+    a.rep = rep; a.sn = sn; a.sd = sd; a.sp = sp;
+    a.hw = static_cast<uint32_t>(hw); a.P = static_cast<uint32_t>(P); a.D = static_cast<uint32_t>(D);
+    a.nb = static_cast<uint32_t>((P + kBlk - 1) / kBlk);
+    a.an_bits = an_bits; a.blockoff_an = blockoff_an; a.act_class = act_class; a.a_ord = a_ord; a.neg_rows = neg_rows;
+    a.proto = proto; a.bank = nullptr; a.class_bank = class_bank; a.nact = nact; a.nq = nq; a.nneg = nneg;
+    a.inv_temp = 1.0f / temperature;
+    a.scale = 1.0f / (static_cast<float>(nq) * static_cast<float>(valid_seg));
+    a.loss_q = loss_q; a.grad_rows = grad_rows; a.anchor_pix = anchor_pix;
+    const int warps = nact * nq;
+    infonce_fwd_kernel<true><<<(warps + 3) / 4, 128, 0, s>>>(a);
+    infonce_loss_kernel<<<1, 256, 0, s>>>(loss_q, warps, a.scale, loss);
+    return check_launch("infonce_forward_sharded", 2);
+}
+
+// ------------------------------------------------------------------ peer-mapped bank shards (CUDA IPC)
+// One cudaMalloc'd shard per rank, exported with cudaIpcGetMemHandle, opened by every other rank of the same box with
+// cudaIpcOpenMemHandle (peer access over NVLink is enabled lazily by the driver).  The handles travel through the
+// host-side process group (u2pl_b200/bank.py); nothing here depends on torch or NCCL.
+extern "C" int u2pl_shard_alloc(int64_t bytes, void **dptr, unsigned char *handle64)
+{
+    if (bytes <= 0 || !dptr || !handle64) return bad_arg("shard_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, static_cast<size_t>(bytes));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, static_cast<size_t>(bytes));
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { if (p) cudaFree(p); set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
+    memcpy(handle64, &h, 64);
+    *dptr = p;
+    return 0;
+}
+
+extern "C" int u2pl_shard_open(const unsigned char *handle64, void **dptr)
+{
+    if (!handle64 || !dptr) return bad_arg("shard_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
+    return 0;
+}
+
+extern "C" int u2pl_shard_close(void *dptr, int owned)
+{
+    if (!dptr) return 0;
+    cudaError_t e = owned ? cudaFree(dptr) : cudaIpcCloseMemHandle(dptr);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
+    return 0;
 }
 
 extern "C" int u2pl_infonce_backward(const float *grad_rows, const int32_t *anchor_pix, int nrows,
