@@ -1,0 +1,83 @@
+"""CPU: a numpy model of csrc/conv_tc.cu's ADDRESSING -- pixel-tile decomposition, per-tap TMA box coordinates with
+zero fill outside the image, the weight matrix's K ordering (tap-major, then channel) including the K blocks that
+straddle a tap boundary when Cin % 64 != 0, and the epilogue's row -> pixel mapping and masks -- against F.conv2d.
+The tensor-core / TMA / barrier mechanics are the flat GEMM's (validated on the GPU); what is new in the conv kernel
+is exactly this index arithmetic, so it is pinned here where it can run without a GPU."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+BM, BN, BK = 128, 128, 64
+
+
+def _box(x, c0, w0, h0, n, tw, th):
+    """4-D TMA box {64 ch, tw, th, 1 image} at signed coordinates; elements outside the tensor read as zero.
+    Returns the [th*tw, 64] tile in the order TMA writes it (w fastest, then h)."""
+    N, H, W, C = x.shape
+    out = np.zeros((th, tw, BK), np.float32)
+    for i in range(th):
+        for j in range(tw):
+            h, w = h0 + i, w0 + j
+            if 0 <= h < H and 0 <= w < W:
+                c1 = min(c0 + BK, C)
+                if c0 < C:
+                    out[i, j, :c1 - c0] = x[n, h, w, c0:c1]
+    return out.reshape(th * tw, BK)
+
+
+def _wbox(wmat, k0, n0):
+    """2-D box {64 K, 128 rows} of the [Cout, R*S*Cin] weight matrix, zero fill outside."""
+    Cout, K = wmat.shape
+    out = np.zeros((BN, BK), np.float32)
+    r1, k1 = min(n0 + BN, Cout), min(k0 + BK, K)
+    if n0 < Cout and k0 < K:
+        out[:r1 - n0, :k1 - k0] = wmat[n0:r1, k0:k1]
+    return out
+
+
+def conv_model(x_nhwc, w_ocrs_c, ksize, dil, flat):
+    N, H, W, Cin = x_nhwc.shape
+    Cout = w_ocrs_c.shape[0]
+    wmat = w_ocrs_c.reshape(Cout, -1)                         # [Cout, R*S*Cin]: memory order of a channels-last weight
+    if flat:                                                  # host wrapper, ksize == 1
+        xv = x_nhwc.reshape(1, 1, N * H * W, Cin)
+        Nimg, Hh, Ww, log2_tw, tiles_h, tiles_w = 1, 1, N * H * W, 7, 1, (N * H * W + BM - 1) // BM
+    else:
+        xv = x_nhwc
+        Nimg, Hh, Ww, log2_tw, tiles_h, tiles_w = N, H, W, 4, (H + 7) // 8, (W + 15) // 16
+    tw, th = 1 << log2_tw, BM >> log2_tw
+    out = np.full((Nimg * Hh * Ww, Cout), np.nan, np.float32)
+    kb_per_tap = (Cin + BK - 1) // BK
+    tiles_img = tiles_h * tiles_w
+    for tm in range(Nimg * tiles_img):
+        img, rem = divmod(tm, tiles_img)
+        h0, w0 = (rem // tiles_w) * th, (rem % tiles_w) * tw
+        for n0 in range(0, Cout, BN):
+            acc = np.zeros((BM, BN), np.float32)
+            for tap in range(ksize * ksize):
+                dh, dw = (tap // ksize - ksize // 2) * dil, (tap % ksize - ksize // 2) * dil
+                for kb in range(kb_per_tap):
+                    a = _box(xv, kb * BK, w0 + dw, h0 + dh, img, tw, th)
+                    b = _wbox(wmat, tap * Cin + kb * BK, n0)
+                    acc += a @ b.T
+            for m in range(BM):                               # epilogue: one thread per accumulator row
+                h, w = h0 + (m >> log2_tw), w0 + (m & (tw - 1))
+                if h < Hh and w < Ww:
+                    pix = (img * Hh + h) * Ww + w
+                    ncol = min(BN, Cout - n0)
+                    assert np.isnan(out[pix, n0]), "pixel written twice"
+                    out[pix, n0:n0 + ncol] = acc[m, :ncol]
+    assert not np.isnan(out).any(), "pixel never written"
+    return out.reshape(N, H, W, Cout)
+
+
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,d", [(2, 72, 11, 19, 40, 3, 1), (1, 64, 20, 17, 136, 3, 3), (2, 8, 9, 9, 8, 3, 12),
+                                                (3, 72, 5, 7, 24, 1, 1), (1, 128, 13, 11, 256, 1, 1)])
+def test_conv_addressing_model(N, Cin, H, W, Cout, k, d):
+    g = torch.Generator().manual_seed(N * 100 + Cin + d)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g)
+    ref = F.conv2d(x, w, None, 1, d * (k // 2), d).permute(0, 2, 3, 1).numpy()
+    got = conv_model(x.permute(0, 2, 3, 1).contiguous().numpy(), w.permute(0, 2, 3, 1).contiguous().numpy(), k, d, flat=(k == 1))
+    assert np.abs(got - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())

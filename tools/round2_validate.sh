@@ -1,0 +1,25 @@
+#!/bin/bash
+# tools/round2_validate.sh -- ONE gpurun call that validates everything written after round 1's GPU minutes ran out
+# and collects the numbers into gpurun_out/ (copy what matters into profiles/ afterwards).
+#   1 GPU :  gpurun --timeout 1500 -- 'bash tools/round2_validate.sh 1'
+#   2 GPUs:  gpurun --gpus 2 --timeout 900 -- 'bash tools/round2_validate.sh 2'
+set -u
+mkdir -p gpurun_out
+OUT=gpurun_out
+if [ "${1:-1}" = "1" ]; then
+  timeout 600 python -m pytest tests -m gpu -x -q                                   > $OUT/r2_pytest_gpu.log 2>&1;      echo "pytest default: $?"
+  U2PL_TC_CONV=1 timeout 300 python -m pytest tests/test_gpu_conv_tc.py -q          > $OUT/r2_pytest_conv_tc.log 2>&1;  echo "pytest conv_tc: $?"
+  timeout 200 python tools/conv_bench.py                                            > $OUT/r2_conv_bench.jsonl 2>$OUT/r2_conv_bench.err; echo "conv_bench: $?"
+  timeout 300 python bench.py --impl eager --steps 5 --warmup 3                     > $OUT/r2_bench_eager.json 2>$OUT/r2_bench_eager.err; echo "bench eager: $?"
+  timeout 300 python bench.py --steps 10 --warmup 3                                 > $OUT/r2_bench_n1.json 2>$OUT/r2_bench_n1.err;       echo "bench ours: $?"
+  U2PL_TC_CONV=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_tcconv.json 2>$OUT/r2_bench_n1_tcconv.err; echo "bench ours+tc_conv: $?"
+else
+  N=$1
+  U2PL_BANK_SHARDED_TEST=1 timeout 300 python -m pytest tests/test_gpu_sharded_bank.py -x -q > $OUT/r2_pytest_sharded.log 2>&1; echo "pytest sharded: $?"
+  for mode in 0 1; do
+    U2PL_BANK_SHARDED=$mode timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+      --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > $OUT/r2_bench_n${N}_sharded${mode}.json 2>$OUT/r2_bench_n${N}_sharded${mode}.err
+    echo "bench N=$N sharded=$mode: $?"
+  done
+fi
+tail -n 3 $OUT/r2_*.log 2>/dev/null
