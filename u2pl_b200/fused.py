@@ -28,7 +28,10 @@ import os
 
 # "tc_conv": eval-mode conv + BN (+residual, +ReLU) through the tcgen05 implicit-GEMM kernel (csrc/conv_tc.cu).
 # Off unless U2PL_TC_CONV=1: the kernel was written after round 1's GPU minutes were spent and has not run on a B200 yet.
-ENABLED = {"bn": True, "wgrad": True, "tc_conv": os.environ.get("U2PL_TC_CONV", "0") == "1"}
+# "wgrad_stack": stride-1 dilated weight gradient as ONE GEMM against nine shifted, zero-padded copies of the (small)
+# output gradient instead of nine GEMMs over cropped copies of the (large) input.  Same status: opt-in, unmeasured.
+ENABLED = {"bn": True, "wgrad": True, "tc_conv": os.environ.get("U2PL_TC_CONV", "0") == "1",
+           "wgrad_stack": os.environ.get("U2PL_WGRAD_STACK", "0") == "1"}
 
 
 def _world():
@@ -208,6 +211,19 @@ class _DilatedConvFn(torch.autograd.Function):
                 hi = min(n_out - 1, (n_in - 1 - off) // s)
                 return lo, hi, off
 
+            if s == 1 and ENABLED["wgrad_stack"]:
+                # dw[co,ky,kx,ci] = sum_q g9[q, (ky,kx), co] * x[q, ci] with g9[q, tap] = g[q - offset(tap)] (zero where
+                # that falls outside the map): x is read in place, only the Co-channel gradient is copied (9 shifted times)
+                g9 = torch.zeros((N, H, W, 9, Co), dtype=gout.dtype, device=x.device)
+                for ky in range(3):
+                    y0, y1, oy = span(ky, H, Ho)
+                    for kx in range(3):
+                        x0, x1, ox = span(kx, W, Wo)
+                        if y1 >= y0 and x1 >= x0:
+                            g9[:, y0 + oy:y1 + oy + 1, x0 + ox:x1 + ox + 1, ky * 3 + kx, :] = gh[:, y0:y1 + 1, x0:x1 + 1, :]
+                dw9 = torch.mm(g9.view(N * H * W, 9 * Co).t(), xh.reshape(N * H * W, Ci)).float()      # [9*Co, Ci]
+                dw = dw9.view(3, 3, Co, Ci).permute(2, 3, 0, 1).to(w.dtype)
+                return dx, dw, None, None
             for ky in range(3):
                 y0, y1, oy = span(ky, H, Ho)
                 if y1 < y0:
