@@ -8,7 +8,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-BM, BN, BK = 128, 128, 64
+BM, BK = 128, 64
 
 
 def _box(x, c0, w0, h0, n, tw, th):
@@ -26,8 +26,8 @@ def _box(x, c0, w0, h0, n, tw, th):
     return out.reshape(th * tw, BK)
 
 
-def _wbox(wmat, k0, n0):
-    """2-D box {64 K, 128 rows} of the [Cout, R*S*Cin] weight matrix, zero fill outside."""
+def _wbox(wmat, k0, n0, BN):
+    """2-D box {64 K, BN rows} of the [Cout, R*S*Cin] weight matrix, zero fill outside."""
     Cout, K = wmat.shape
     out = np.zeros((BN, BK), np.float32)
     r1, k1 = min(n0 + BN, Cout), min(k0 + BK, K)
@@ -40,6 +40,7 @@ def conv_model(x_nhwc, w_ocrs_c, ksize, dil, flat):
     N, H, W, Cin = x_nhwc.shape
     Cout = w_ocrs_c.shape[0]
     wmat = w_ocrs_c.reshape(Cout, -1)                         # [Cout, R*S*Cin]: memory order of a channels-last weight
+    BN = 256 if Cout > 128 else 128                           # host wrapper's channel-tile choice
     if flat:                                                  # host wrapper, ksize == 1
         xv = x_nhwc.reshape(1, 1, N * H * W, Cin)
         Nimg, Hh, Ww, log2_tw, tiles_h, tiles_w = 1, 1, N * H * W, 7, 1, (N * H * W + BM - 1) // BM
@@ -59,7 +60,7 @@ def conv_model(x_nhwc, w_ocrs_c, ksize, dil, flat):
                 dh, dw = (tap // ksize - ksize // 2) * dil, (tap % ksize - ksize // 2) * dil
                 for kb in range(kb_per_tap):
                     a = _box(xv, kb * BK, w0 + dw, h0 + dh, img, tw, th)
-                    b = _wbox(wmat, tap * Cin + kb * BK, n0)
+                    b = _wbox(wmat, tap * Cin + kb * BK, n0, BN)
                     acc += a @ b.T
             for m in range(BM):                               # epilogue: one thread per accumulator row
                 h, w = h0 + (m >> log2_tw), w0 + (m & (tw - 1))

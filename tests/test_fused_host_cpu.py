@@ -47,3 +47,19 @@ def test_conv_bn_act_falls_back_off_gpu():
         got = fused.conv_bn_act(x, conv, bn, relu, r)
         assert torch.allclose(got, relu(bn(conv(x)) + r), atol=1e-6)
     assert fused.ENABLED["tc_conv"] is False                      # opt-in only (U2PL_TC_CONV=1)
+
+
+@pytest.mark.parametrize("k,d", [(1, 1), (3, 1), (3, 2), (3, 5)])
+def test_dgrad_weight_identity(k, d):
+    """The data gradient of a stride-1 'same' convolution is the convolution of the output gradient with
+    fused.dgrad_weight(w) -- what _ConvTCFn.backward feeds to the implicit-GEMM kernel."""
+    import torch.nn.functional as F
+    torch.manual_seed(k + d)
+    x = torch.randn(2, 5, 9, 11, requires_grad=True)
+    w = torch.randn(7, 5, k, k)
+    pad = d * (k // 2)
+    y = F.conv2d(x, w, None, 1, pad, d)
+    g = torch.randn_like(y)
+    y.backward(g)
+    dx = F.conv2d(g, fused.dgrad_weight(w), None, 1, pad, d)
+    assert torch.allclose(dx, x.grad, atol=1e-4)

@@ -84,3 +84,21 @@ def test_eval_model_same_with_and_without_tc_conv():
     for k in ("pred", "rep"):
         a, b = outs[False][k], outs[True][k]
         assert (a - b).norm() <= 0.03 * a.norm(), (k, float((a - b).norm() / a.norm()))
+
+
+@pytest.mark.parametrize("k,d,Cin,Cout", [(3, 2, 256, 256), (1, 1, 256, 1024), (3, 12, 512, 256)])
+def test_conv_tc_fn_forward_and_data_gradient(k, d, Cin, Cout):
+    """fused._ConvTCFn (U2PL_TC_TRAIN path): forward and dx on the implicit-GEMM kernel, dw through ATen."""
+    from u2pl_b200 import fused
+    torch.manual_seed(k * 100 + d)
+    x = _cl(torch.randn(2, Cin, 33, 35, device="cuda").bfloat16()).requires_grad_(True)
+    w = _cl((torch.randn(Cout, Cin, k, k, device="cuda") / (Cin * k * k) ** 0.5).bfloat16()).requires_grad_(True)
+    y = fused._ConvTCFn.apply(x, w, d)
+    g = _cl(torch.randn_like(y))
+    y.backward(g)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    torch.backends.cudnn.allow_tf32 = False
+    yr = F.conv2d(xr, wr, None, 1, d * (k // 2), d)
+    yr.backward(g.float())
+    for a, b in ((y, yr), (x.grad, xr.grad), (w.grad, wr.grad)):
+        assert (a.float() - b).abs().max() <= 1.5e-2 * max(1.0, b.abs().max().item())

@@ -13,6 +13,7 @@ if [ "${1:-1}" = "1" ]; then
   timeout 300 python bench.py --impl eager --steps 5 --warmup 3                     > $OUT/r2_bench_eager.json 2>$OUT/r2_bench_eager.err; echo "bench eager: $?"
   timeout 300 python bench.py --steps 10 --warmup 3                                 > $OUT/r2_bench_n1.json 2>$OUT/r2_bench_n1.err;       echo "bench ours: $?"
   U2PL_TC_CONV=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_tcconv.json 2>$OUT/r2_bench_n1_tcconv.err; echo "bench ours+tc_conv: $?"
+  U2PL_TC_CONV=1 U2PL_TC_TRAIN=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_tctrain.json 2>$OUT/r2_bench_n1_tctrain.err; echo "bench ours+tc_conv+tc_train: $?"
   U2PL_WGRAD_STACK=1 timeout 200 python -m pytest tests/test_gpu_fused.py -q -k dilated > $OUT/r2_pytest_wgrad_stack.log 2>&1; echo "pytest wgrad_stack: $?"
   U2PL_WGRAD_STACK=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_wgradstack.json 2>$OUT/r2_bench_n1_wgradstack.err; echo "bench ours+wgrad_stack: $?"
 else

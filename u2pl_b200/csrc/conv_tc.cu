@@ -30,11 +30,14 @@
 namespace u2pl {
 
 namespace convtc {
-constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 4;
-constexpr int kTileABytes = kBM * kBK * 2, kTileBBytes = kBN * kBK * 2;
+constexpr int kBM = 128, kBK = 64, kStages = 4;
+constexpr int kTileABytes = kBM * kBK * 2;
 constexpr int kThreads = 192;
-constexpr int kTmemCols = 128;
 }  // namespace convtc
+// The output-channel tile kBN is a template parameter: 128 (layers with Cout <= 128) or 256.  With a 128x128 tile one
+// k-block costs 256 tensor-core cycles but needs 32 KB of shared-memory fill -- right at the per-SM L2->smem rate, which
+// is why the flat 128x128 GEMM stops at ~0.6 of cuBLAS; a 128x256 tile doubles the MMA work per A byte (48 KB per 512
+// cycles) and uses all 512 TMEM columns for the two accumulator stages.
 
 struct ConvParams {
     int Nimg, H, W, Cin, Cout;        // logical NHWC geometry the tensor map was built from (flat 1x1: Nimg=H=1, W=N*H*W)
@@ -47,10 +50,12 @@ struct ConvParams {
     __nv_bfloat16 *D;
 };
 
+template <int kBN>
 __global__ void __launch_bounds__(convtc::kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, ConvParams p)
 {
     using namespace convtc;
+    constexpr int kTileBBytes = kBN * kBK * 2, kTmemCols = kBN;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t *sA = smem, *sB = smem + kStages * kTileABytes;
@@ -59,7 +64,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint64_t *tmem_full = empty + kStages;            // [2]
     uint64_t *tmem_empty = tmem_full + 2;             // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-    float *s_par = reinterpret_cast<float *>(tmem_slot + 2);      // [2 stages][scale 128 | shift 128]
+    float *s_par = reinterpret_cast<float *>(tmem_slot + 2);      // [2 stages][scale kBN | shift kBN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tw = 1 << p.log2_tw, th = kBM >> p.log2_tw;
@@ -143,9 +148,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const uint32_t acc = tile_i & 1, use = tile_i >> 1;
             float *s_scale = s_par + acc * 2 * kBN, *s_shift = s_scale + kBN;
             if (affine) {
-                const int e = threadIdx.x - 64, c = n0 + e;
-                s_scale[e] = (p.scale && c < p.Cout) ? __ldg(p.scale + c) : 1.0f;
-                s_shift[e] = (p.shift && c < p.Cout) ? __ldg(p.shift + c) : 0.0f;
+                for (int e = threadIdx.x - 64; e < kBN; e += 128) {
+                    const int c = n0 + e;
+                    s_scale[e] = (p.scale && c < p.Cout) ? __ldg(p.scale + c) : 1.0f;
+                    s_shift[e] = (p.shift && c < p.Cout) ? __ldg(p.shift + c) : 0.0f;
+                }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             mbar_wait(tmem_full + acc, use & 1);
@@ -217,13 +224,13 @@ static bool make_map_nhwc(CUtensorMap *map, const void *base, int64_t n, int64_t
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static bool make_map_weight(CUtensorMap *map, const void *base, int64_t cout, int64_t ktot)
+static bool make_map_weight(CUtensorMap *map, const void *base, int64_t cout, int64_t ktot, int bn)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(cout)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(convtc::kBK), static_cast<cuuint32_t>(convtc::kBN)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(convtc::kBK), static_cast<cuuint32_t>(bn)};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -258,24 +265,34 @@ extern "C" int u2pl_conv_bf16_nhwc(const void *x, const void *wgt, void *out, in
         p.log2_tw = 4; p.tiles_h = (p.H + 7) / 8; p.tiles_w = (p.W + 15) / 16;
         ok = make_map_nhwc(&mx, x, n, h, w, cin, 8, 16);
     }
-    ok = ok && make_map_weight(&mw, wgt, cout, static_cast<int64_t>(ksize) * ksize * cin);
+    // channel tile: 256 when the layer has more than 128 output channels (U2PL_CONV_BN=128 forces the narrow tile)
+    static const int forced_bn = [] { const char *e = getenv("U2PL_CONV_BN"); return e ? atoi(e) : 0; }();
+    const int bn = (forced_bn == 128 || forced_bn == 256) ? forced_bn : (cout > 128 ? 256 : 128);
+    ok = ok && make_map_weight(&mw, wgt, cout, static_cast<int64_t>(ksize) * ksize * cin, bn);
     if (!ok) { set_error("conv_bf16_nhwc: cuTensorMapEncodeTiled failed"); return U2PL_E_BADARG; }
     p.Cin = static_cast<int>(cin); p.Cout = static_cast<int>(cout);
     p.R = p.S = ksize; p.dil = dilation;
     p.scale = scale; p.shift = shift; p.residual = static_cast<const __nv_bfloat16 *>(residual); p.relu = relu;
     p.D = static_cast<__nv_bfloat16 *>(out);
-    const size_t smem = static_cast<size_t>(kStages) * (kTileABytes + kTileBBytes) + 1024 + 256 + 4 * kBN * sizeof(float);
+    const size_t smem = static_cast<size_t>(kStages) * (kTileABytes + bn * kBK * 2) + 1024 + 256 + 4 * bn * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(kStages * (kTileABytes + 128 * kBK * 2) + 1024 + 256 + 4 * 128 * sizeof(float)));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(kStages * (kTileABytes + 256 * kBK * 2) + 1024 + 256 + 4 * 256 * sizeof(float)));
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
         configured = true;
     }
-    const long long tiles = static_cast<long long>(p.Nimg) * p.tiles_h * p.tiles_w * ((cout + kBN - 1) / kBN);
+    const long long tiles = static_cast<long long>(p.Nimg) * p.tiles_h * p.tiles_w * ((cout + bn - 1) / bn);
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned g = static_cast<unsigned>(tiles < sms ? tiles : sms);
-    conv_tc_kernel<<<g, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(mx, mw, p);
+    if (bn == 256)
+        conv_tc_kernel<256><<<g, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(mx, mw, p);
+    else
+        conv_tc_kernel<128><<<g, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(mx, mw, p);
     return check_launch("conv_bf16_nhwc");
 }

@@ -30,8 +30,12 @@ import os
 # Off unless U2PL_TC_CONV=1: the kernel was written after round 1's GPU minutes were spent and has not run on a B200 yet.
 # "wgrad_stack": stride-1 dilated weight gradient as ONE GEMM against nine shifted, zero-padded copies of the (small)
 # output gradient instead of nine GEMMs over cropped copies of the (large) input.  Same status: opt-in, unmeasured.
+# "tc_train": train-mode forward AND data gradient of every eligible stride-1 convolution through the same kernel
+# (the data gradient of a stride-1 "same" convolution is a convolution of the output gradient with the flipped,
+# transposed weight); weight gradients stay with cuDNN / the GEMM paths above.  Same status.
 ENABLED = {"bn": True, "wgrad": True, "tc_conv": os.environ.get("U2PL_TC_CONV", "0") == "1",
-           "wgrad_stack": os.environ.get("U2PL_WGRAD_STACK", "0") == "1"}
+           "wgrad_stack": os.environ.get("U2PL_WGRAD_STACK", "0") == "1",
+           "tc_train": os.environ.get("U2PL_TC_TRAIN", "0") == "1"}
 
 
 def _world():
@@ -126,6 +130,46 @@ def bn_act(x, bn, relu=None, residual=None):
     return relu(y) if isinstance(relu, nn.Module) else F.relu(y)
 
 
+def dgrad_weight(w):
+    """Weight of the convolution that maps the output gradient of a stride-1 "same" convolution to its input gradient:
+    w'[ci, co, r, s] = w[co, ci, k-1-r, k-1-s] (same dilation and padding)."""
+    return w.transpose(0, 1).flip(2, 3)
+
+
+class _ConvTCFn(torch.autograd.Function):
+    """Stride-1 "same" convolution of channels-last bf16 tensors on the tcgen05 implicit-GEMM kernel, forward and data
+    gradient; the weight gradient through ATen (cuDNN)."""
+
+    @staticmethod
+    def forward(ctx, x, w, dilation):
+        from .ops import conv_bf16_nhwc
+        ctx.save_for_backward(x, w)
+        ctx.dilation = dilation
+        return conv_bf16_nhwc(x, w, dilation)
+
+    @staticmethod
+    def backward(ctx, gout):
+        from .ops import conv_bf16_nhwc
+        x, w = ctx.saved_tensors
+        d, k = ctx.dilation, w.shape[2]
+        gout = gout.contiguous(memory_format=torch.channels_last)
+        dx = conv_bf16_nhwc(gout, dgrad_weight(w), d) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            pad = d * (k // 2)
+            dw = torch.ops.aten.convolution_backward(gout, x, w, None, [1, 1], [pad, pad], [d, d], False, [0, 0], 1,
+                                                     [False, True, False])[1]
+        return dx, dw, None
+
+
+def _tc_geometry_ok(x, conv):
+    k, d = conv.kernel_size[0], conv.dilation[0]
+    return (_is_cl_bf16(x) and isinstance(conv, nn.Conv2d) and conv.kernel_size in ((1, 1), (3, 3))
+            and conv.stride == (1, 1) and conv.dilation == (d, d) and conv.padding == (d * (k // 2), d * (k // 2))
+            and conv.groups == 1 and conv.bias is None and conv.padding_mode == "zeros"
+            and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0)
+
+
 def _tc_conv_ok(x, conv, bn, residual):
     k, d = conv.kernel_size[0], conv.dilation[0]
     return (ENABLED["tc_conv"] and not bn.training and not torch.is_grad_enabled() and _is_cl_bf16(x)
@@ -141,6 +185,9 @@ def conv_bn_act(x, conv, bn, relu=None, residual=None):
     bf16 activations: ONE implicit-GEMM kernel with the folded BatchNorm, the residual and the ReLU in its epilogue;
     otherwise the convolution module followed by `bn_act`."""
     if not _tc_conv_ok(x, conv, bn, residual):
+        if ENABLED["tc_train"] and type(conv) is nn.Conv2d and _tc_geometry_ok(x, conv):   # train mode / autograd on
+            y = _ConvTCFn.apply(x, conv.weight.to(torch.bfloat16), conv.dilation[0])
+            return bn_act(y, bn, relu, residual)
         return bn_act(conv(x), bn, relu, residual)
     from .ops import conv_bf16_nhwc
     lib = _lib.load()
@@ -159,7 +206,8 @@ def run_sequential(seq, x):
     while i < len(mods):
         m = mods[i]
         if isinstance(m, nn.Conv2d) and i + 1 < len(mods) and isinstance(mods[i + 1], (nn.BatchNorm2d, nn.SyncBatchNorm)) \
-                and _tc_conv_ok(x, m, mods[i + 1], None):
+                and (_tc_conv_ok(x, m, mods[i + 1], None)
+                     or (ENABLED["tc_train"] and type(m) is nn.Conv2d and _tc_geometry_ok(x, m))):
             nxt = mods[i + 2] if i + 2 < len(mods) else None
             x = conv_bn_act(x, m, mods[i + 1], nxt if isinstance(nxt, nn.ReLU) else None)
             i += 3 if isinstance(nxt, nn.ReLU) else 2
@@ -186,6 +234,9 @@ class _DilatedConvFn(torch.autograd.Function):
     def forward(ctx, x, w, dilation, stride):
         ctx.save_for_backward(x, w)
         ctx.cfg = (dilation, stride)
+        if ENABLED["tc_train"] and stride == 1 and _is_cl_bf16(x):
+            from .ops import conv_bf16_nhwc
+            return conv_bf16_nhwc(x, w, dilation)
         return F.conv2d(x, w, None, stride, dilation, dilation)
 
     @staticmethod
@@ -194,7 +245,10 @@ class _DilatedConvFn(torch.autograd.Function):
         d, s = ctx.cfg
         gout = gout.contiguous(memory_format=torch.channels_last)
         dx = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and ENABLED["tc_train"] and s == 1 and _is_cl_bf16(gout):
+            from .ops import conv_bf16_nhwc
+            dx = conv_bf16_nhwc(gout, dgrad_weight(w), d)
+        elif ctx.needs_input_grad[0]:
             dx = torch.ops.aten.convolution_backward(gout, x, w, None, [s, s], [d, d], [d, d], False, [0, 0], 1,
                                                      [True, False, False])[0]
         dw = None
