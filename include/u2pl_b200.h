@@ -289,6 +289,16 @@ int u2pl_conv_bf16_nhwc(const void *x, const void *wgt, void *out, int64_t n, in
                         int64_t cout, int ksize, int dilation, const float *scale, const float *shift,
                         const void *residual, int relu, void *stream);
 
+/* Train-mode variant: raw convolution output (bf16) PLUS the per-channel batch statistics of the stored values in the
+ * same pass -- the epilogue accumulates sum and sum of squares per (pixel tile, channel) into stat_part
+ * [u2pl_conv_stat_parts(n,h,w,ksize)][2][cout] and a second tiny kernel reduces them to sums [2][cout], the input
+ * u2pl_bn_finalize expects.  replaces: conv (resnet.py:25-41) + the statistics pass of F.batch_norm(training=True)
+ * (u2pl_bn_stats) on the student / train-mode teacher forwards (train_semi.py:340-341, 362-364). */
+int64_t u2pl_conv_stat_parts(int64_t n, int64_t h, int64_t w, int ksize);
+int u2pl_conv_bf16_nhwc_stats(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w,
+                              int64_t cin, int64_t cout, int ksize, int dilation, float *stat_part, float *sums,
+                              void *stream);
+
 #ifdef __cplusplus
 }
 #endif

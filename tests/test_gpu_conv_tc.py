@@ -102,3 +102,55 @@ def test_conv_tc_fn_forward_and_data_gradient(k, d, Cin, Cout):
     yr.backward(g.float())
     for a, b in ((y, yr), (x.grad, xr.grad), (w.grad, wr.grad)):
         assert (a.float() - b).abs().max() <= 1.5e-2 * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,d", [(2, 256, 65, 65, 256, 3, 2), (3, 64, 33, 31, 128, 3, 1), (2, 1024, 17, 19, 256, 1, 1),
+                                                (2, 72, 20, 24, 40, 3, 3)])
+def test_conv_stats_epilogue(N, Cin, H, W, Cout, k, d):
+    """kStats epilogue: output identical to the plain kernel, sums = per-channel sum / sum of squares of the stored values."""
+    from u2pl_b200 import ops
+    torch.manual_seed(Cin + d)
+    x = _cl(torch.randn(N, Cin, H, W, device="cuda").bfloat16())
+    w = _cl((torch.randn(Cout, Cin, k, k, device="cuda") / (Cin * k * k) ** 0.5).bfloat16())
+    y0 = ops.conv_bf16_nhwc(x, w, d)
+    y, sums = ops.conv_bf16_nhwc_stats(x, w, d)
+    assert torch.equal(y, y0)
+    yf = y.float()
+    ref = torch.stack([yf.sum(dim=(0, 2, 3)), (yf * yf).sum(dim=(0, 2, 3))])
+    assert torch.allclose(sums, ref, rtol=2e-4, atol=2e-3 * ref.abs().max().item() ** 0.5)
+
+
+def test_train_mode_model_with_tc_train_matches_default():
+    """Whole mirror encoder in train mode: U2PL_TC_TRAIN path (conv + statistics epilogue, tcgen05 data gradients) against
+    the default path (cuDNN + u2pl_bn_stats) from the same weights: features and gradients to bf16 noise."""
+    import copy
+    import u2pl_b200
+    from u2pl_b200 import fused
+    u2pl_b200.install()
+    from u2pl.models.model_helper import ModelBuilder
+    net = {"num_classes": 21, "sync_bn": False, "ema_decay": 0.99,
+           "encoder": {"type": "u2pl.models.resnet.resnet50",
+                       "kwargs": {"multi_grid": True, "zero_init_residual": False, "fpn": True,
+                                  "replace_stride_with_dilation": [False, True, True], "pretrained": False}},
+           "decoder": {"type": "u2pl.models.decoder.dec_deeplabv3_plus", "kwargs": {"inner_planes": 256, "dilations": [12, 24, 36]}}}
+    torch.manual_seed(0)
+    ma = ModelBuilder(copy.deepcopy(net)).cuda().to(memory_format=torch.channels_last)
+    mb = copy.deepcopy(ma)
+    x = _cl(torch.randn(4, 3, 97, 97, device="cuda"))
+    res = []
+    for m, flag in ((ma, False), (mb, True)):
+        fused.ENABLED["tc_train"] = flag
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                feats = m.encoder(x)
+            sum(t.float().pow(2).mean() for t in feats).backward()
+        finally:
+            fused.ENABLED["tc_train"] = False
+        res.append((feats, dict(m.named_parameters()), dict(m.named_buffers())))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert (a.float() - b.float()).norm() <= 0.03 * a.float().norm()
+    for name in ("encoder.layer4.2.conv2.weight", "encoder.layer3.2.conv1.weight", "encoder.layer1.0.bn1.weight", "encoder.conv1.3.weight"):
+        ga, gb = res[0][1][name].grad.float(), res[1][1][name].grad.float()
+        assert (ga - gb).norm() <= 0.08 * ga.norm(), name
+    ra, rb = res[0][2]["encoder.layer2.1.bn2.running_var"], res[1][2]["encoder.layer2.1.bn2.running_var"]
+    assert (ra - rb).abs().max() <= 0.02 * ra.abs().max().item()

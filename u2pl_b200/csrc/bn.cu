@@ -357,6 +357,12 @@ constexpr int kBnParts = 148 * 4;        // partial-sum blocks: enough 16 B load
 
 extern "C" int64_t u2pl_bn_parts(void) { return kBnParts; }
 
+int u2pl::bn_reduce_parts(const float *partial, int nparts, int c2, float *sums, void *stream)
+{
+    bn_reduce_kernel<<<(c2 + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, nparts, c2, sums);
+    return check_launch("bn_reduce_parts");
+}
+
 extern "C" int u2pl_bn_stats(const void *x, int64_t M, int64_t C, float *partial, float *sums, void *stream)
 {
     if (!bn_shape_ok(M, C)) return bad_arg("bn_stats: need C % 8 == 0, C/8 a divisor of 256, C <= 2048");

@@ -23,6 +23,8 @@ inline int check_launch(const char *what, int n = 1)
     return 0;
 }
 
+int bn_reduce_parts(const float *partial, int nparts, int c2, float *sums, void *stream);   // bn.cu: [nparts][c2] -> [c2]
+
 inline int bad_arg(const char *msg) { set_error(msg); return U2PL_E_BADARG; }
 
 constexpr int kNumSMs = 148;               // B200

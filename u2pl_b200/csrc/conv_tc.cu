@@ -48,9 +48,10 @@ struct ConvParams {
     const __nv_bfloat16 *residual;    // same layout as D, or null
     int relu;
     __nv_bfloat16 *D;
+    float *stat_part;                 // kStats only: [pixel tiles][2][Cout] per-tile sum / sum of squares of the STORED values
 };
 
-template <int kBN>
+template <int kBN, bool kStats>
 __global__ void __launch_bounds__(convtc::kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, ConvParams p)
 {
@@ -65,6 +66,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint64_t *tmem_empty = tmem_full + 2;             // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
     float *s_par = reinterpret_cast<float *>(tmem_slot + 2);      // [2 stages][scale kBN | shift kBN]
+    float *s_tr = s_par + 4 * kBN;                                // kStats: [4 warps][32 rows][33] transpose buffers
+    float *s_red = s_tr + 4 * 32 * 33;                            // kStats: [4 warps][kBN][2] per-warp column sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tw = 1 << p.log2_tw, th = kBM >> p.log2_tw;
@@ -167,6 +170,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     if (lane == 0) mbar_arrive(tmem_empty + acc);
                 }
                 const int c0 = n0 + j * 32;
+                float *trow = s_tr + (q * 32 + lane) * 33;        // this thread's row of its warp's transpose buffer
+                if (kStats && !(live && c0 + 32 <= p.Cout)) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) trow[e] = 0.0f;  // dead rows / channels beyond Cout contribute nothing
+                }
                 if (live) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -198,9 +206,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
                             for (int e = 0; e < 4; ++e) oh[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
                             *reinterpret_cast<uint4 *>(p.D + off) = o;
+                            if (kStats) {             // statistics of the values as stored (bf16-rounded), like bn_stats
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = __bfloat1622float2(oh[e]);
+                                    trow[g * 8 + 2 * e] = f.x;
+                                    trow[g * 8 + 2 * e + 1] = f.y;
+                                }
+                            }
                         }
                     }
                 }
+                if (kStats) {                         // column sums over this warp's 32 rows: lane c owns column c0 + c
+                    __syncwarp();
+                    const float *tcol = s_tr + q * 32 * 33 + lane;
+                    float cs = 0.0f, cq = 0.0f;
+#pragma unroll
+                    for (int r2 = 0; r2 < 32; ++r2) {
+                        const float xv = tcol[r2 * 33];
+                        cs += xv;
+                        cq = fmaf(xv, xv, cq);
+                    }
+                    s_red[(q * kBN + j * 32 + lane) * 2] = cs;
+                    s_red[(q * kBN + j * 32 + lane) * 2 + 1] = cq;
+                    __syncwarp();
+                }
+            }
+            if (kStats) {                             // 4 warps -> one partial per (pixel tile, channel)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int e = threadIdx.x - 64; e < kBN; e += 128) {
+                    const int c = n0 + e;
+                    if (c < p.Cout) {
+                        float a = 0.0f, b = 0.0f;
+#pragma unroll
+                        for (int k2 = 0; k2 < 4; ++k2) { a += s_red[(k2 * kBN + e) * 2]; b += s_red[(k2 * kBN + e) * 2 + 1]; }
+                        p.stat_part[(static_cast<size_t>(tm) * 2) * p.Cout + c] = a;
+                        p.stat_part[(static_cast<size_t>(tm) * 2 + 1) * p.Cout + c] = b;
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
         }
     }
@@ -241,9 +285,9 @@ static bool make_map_weight(CUtensorMap *map, const void *base, int64_t cout, in
 
 using namespace u2pl;
 
-extern "C" int u2pl_conv_bf16_nhwc(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w, int64_t cin,
-                                   int64_t cout, int ksize, int dilation, const float *scale, const float *shift,
-                                   const void *residual, int relu, void *stream)
+static int conv_launch(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout,
+                       int ksize, int dilation, const float *scale, const float *shift, const void *residual, int relu,
+                       float *stat_part, const char *what, void *stream)
 {
     using namespace convtc;
     if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || (cin % 8) || (cout % 8) || (ksize != 1 && ksize != 3) || dilation < 1)
@@ -274,25 +318,56 @@ extern "C" int u2pl_conv_bf16_nhwc(const void *x, const void *wgt, void *out, in
     p.R = p.S = ksize; p.dil = dilation;
     p.scale = scale; p.shift = shift; p.residual = static_cast<const __nv_bfloat16 *>(residual); p.relu = relu;
     p.D = static_cast<__nv_bfloat16 *>(out);
-    const size_t smem = static_cast<size_t>(kStages) * (kTileABytes + bn * kBK * 2) + 1024 + 256 + 4 * bn * sizeof(float);
+    p.stat_part = stat_part;
+    auto smem_for = [](int b, bool stats) {
+        return static_cast<size_t>(kStages) * (kTileABytes + b * kBK * 2) + 1024 + 256 + 4 * b * sizeof(float) +
+               (stats ? (4 * 32 * 33 + 4 * b * 2) * sizeof(float) : 0);
+    };
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(kStages * (kTileABytes + 128 * kBK * 2) + 1024 + 256 + 4 * 128 * sizeof(float)));
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(kStages * (kTileABytes + 256 * kBK * 2) + 1024 + 256 + 4 * 256 * sizeof(float)));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_for(128, false)));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_for(256, false)));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_for(128, true)));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_for(256, true)));
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
         configured = true;
     }
+    const bool stats = stat_part != nullptr;
+    const size_t smem = smem_for(bn, stats);
     const long long tiles = static_cast<long long>(p.Nimg) * p.tiles_h * p.tiles_w * ((cout + bn - 1) / bn);
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned g = static_cast<unsigned>(tiles < sms ? tiles : sms);
-    if (bn == 256)
-        conv_tc_kernel<256><<<g, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(mx, mw, p);
-    else
-        conv_tc_kernel<128><<<g, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(mx, mw, p);
-    return check_launch("conv_bf16_nhwc");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (bn == 256 && stats) conv_tc_kernel<256, true><<<g, kThreads, smem, st>>>(mx, mw, p);
+    else if (bn == 256) conv_tc_kernel<256, false><<<g, kThreads, smem, st>>>(mx, mw, p);
+    else if (stats) conv_tc_kernel<128, true><<<g, kThreads, smem, st>>>(mx, mw, p);
+    else conv_tc_kernel<128, false><<<g, kThreads, smem, st>>>(mx, mw, p);
+    return check_launch(what);
+}
+
+extern "C" int u2pl_conv_bf16_nhwc(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w, int64_t cin,
+                                   int64_t cout, int ksize, int dilation, const float *scale, const float *shift,
+                                   const void *residual, int relu, void *stream)
+{
+    return conv_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, scale, shift, residual, relu, nullptr,
+                       "conv_bf16_nhwc", stream);
+}
+
+extern "C" int64_t u2pl_conv_stat_parts(int64_t n, int64_t h, int64_t w, int ksize)
+{
+    if (ksize == 1) return (n * h * w + convtc::kBM - 1) / convtc::kBM;
+    return n * ((h + 7) / 8) * ((w + 15) / 16);
+}
+
+extern "C" int u2pl_conv_bf16_nhwc_stats(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w,
+                                         int64_t cin, int64_t cout, int ksize, int dilation, float *stat_part, float *sums,
+                                         void *stream)
+{
+    if (!stat_part || !sums) return bad_arg("conv_bf16_nhwc_stats: stat_part and sums are required");
+    int rc = conv_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, nullptr, nullptr, nullptr, 0, stat_part,
+                         "conv_bf16_nhwc_stats", stream);
+    if (rc != 0) return rc;
+    return bn_reduce_parts(stat_part, static_cast<int>(u2pl_conv_stat_parts(n, h, w, ksize)), static_cast<int>(2 * cout), sums, stream);
 }

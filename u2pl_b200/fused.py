@@ -47,11 +47,14 @@ def _is_cl_bf16(x):
             and x.is_contiguous(memory_format=torch.channels_last))
 
 
-def _bn_ok(x, bn):
-    C = x.shape[1]
-    return (ENABLED["bn"] and _is_cl_bf16(x) and isinstance(bn, (nn.BatchNorm2d, nn.SyncBatchNorm))
+def _bn_channels_ok(C, bn):
+    return (ENABLED["bn"] and isinstance(bn, (nn.BatchNorm2d, nn.SyncBatchNorm))
             and C % 8 == 0 and C <= 2048 and 256 % (C // 8) == 0 and bn.momentum is not None
             and bn.track_running_stats)
+
+
+def _bn_ok(x, bn):
+    return _is_cl_bf16(x) and _bn_channels_ok(x.shape[1], bn)
 
 
 def _scratch(dev, C):
@@ -62,7 +65,7 @@ def _scratch(dev, C):
 
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, bn, relu, sync):
+    def forward(ctx, x, weight, bias, residual, bn, relu, sync, sums_in=None):
         lib = _lib.load()
         N, C, H, W = x.shape
         M = N * H * W
@@ -72,8 +75,11 @@ class _BNAct(torch.autograd.Function):
         training = bn.training
         count = float(M)
         if training:
-            partial, sums = _scratch(dev, C)
-            _lib.check(lib.u2pl_bn_stats(_p(x), M, C, _p(partial), _p(sums), _stream()), "u2pl_bn_stats")
+            if sums_in is None:
+                partial, sums = _scratch(dev, C)
+                _lib.check(lib.u2pl_bn_stats(_p(x), M, C, _p(partial), _p(sums), _stream()), "u2pl_bn_stats")
+            else:                                      # statistics already accumulated by the producing conv's epilogue
+                sums = sums_in
             if sync:                                   # SyncBN: global sums; every rank holds the same number of
                 dist.all_reduce(sums)                  # pixels (same per-GPU batch and crop, as in the reference configs)
                 count = float(M) * _world()
@@ -114,14 +120,16 @@ class _BNAct(torch.autograd.Function):
         _lib.check(lib.u2pl_bn_backward_elemt(_p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(weight), _p(sums),
                                               ctypes.c_double(count), M, C, _p(coef), _p(dx), _p(dres), _stream()),
                    "u2pl_bn_backward_elemt")
-        return dx, dweight, dbias, dres, None, None, None
+        return dx, dweight, dbias, dres, None, None, None, None
 
 
-def bn_act(x, bn, relu=None, residual=None):
-    """relu: an nn.ReLU module (or True) to fuse, or None.  residual: tensor added before the ReLU."""
+def bn_act(x, bn, relu=None, residual=None, sums=None):
+    """relu: an nn.ReLU module (or True) to fuse, or None.  residual: tensor added before the ReLU.
+    sums: optional [2,C] batch sums of x from the producing convolution's epilogue (train mode)."""
     if _bn_ok(x, bn) and (residual is None or _is_cl_bf16(residual)):
         sync = isinstance(bn, nn.SyncBatchNorm) and bn.training and _world() > 1
-        return _BNAct.apply(x, bn.weight, bn.bias, residual, bn, relu is not None and relu is not False, sync)
+        return _BNAct.apply(x, bn.weight, bn.bias, residual, bn, relu is not None and relu is not False, sync,
+                            sums if bn.training else None)
     y = bn(x)
     if residual is not None:
         y = y + residual
@@ -141,14 +149,18 @@ class _ConvTCFn(torch.autograd.Function):
     gradient; the weight gradient through ATen (cuDNN)."""
 
     @staticmethod
-    def forward(ctx, x, w, dilation):
-        from .ops import conv_bf16_nhwc
+    def forward(ctx, x, w, dilation, want_stats=False):
+        from .ops import conv_bf16_nhwc, conv_bf16_nhwc_stats
         ctx.save_for_backward(x, w)
         ctx.dilation = dilation
-        return conv_bf16_nhwc(x, w, dilation)
+        if not want_stats:
+            return conv_bf16_nhwc(x, w, dilation)
+        y, sums = conv_bf16_nhwc_stats(x, w, dilation)
+        ctx.mark_non_differentiable(sums)
+        return y, sums
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, gout, *unused):
         from .ops import conv_bf16_nhwc
         x, w = ctx.saved_tensors
         d, k = ctx.dilation, w.shape[2]
@@ -159,7 +171,7 @@ class _ConvTCFn(torch.autograd.Function):
             pad = d * (k // 2)
             dw = torch.ops.aten.convolution_backward(gout, x, w, None, [1, 1], [pad, pad], [d, d], False, [0, 0], 1,
                                                      [False, True, False])[1]
-        return dx, dw, None
+        return dx, dw, None, None
 
 
 def _tc_geometry_ok(x, conv):
@@ -186,6 +198,9 @@ def conv_bn_act(x, conv, bn, relu=None, residual=None):
     otherwise the convolution module followed by `bn_act`."""
     if not _tc_conv_ok(x, conv, bn, residual):
         if ENABLED["tc_train"] and type(conv) is nn.Conv2d and _tc_geometry_ok(x, conv):   # train mode / autograd on
+            if bn.training and _bn_channels_ok(conv.out_channels, bn):
+                y, sums = _ConvTCFn.apply(x, conv.weight.to(torch.bfloat16), conv.dilation[0], True)
+                return bn_act(y, bn, relu, residual, sums=sums)
             y = _ConvTCFn.apply(x, conv.weight.to(torch.bfloat16), conv.dilation[0])
             return bn_act(y, bn, relu, residual)
         return bn_act(conv(x), bn, relu, residual)

@@ -302,3 +302,23 @@ def conv_bf16_nhwc(x, weight, dilation=1, scale=None, shift=None, residual=None,
                                  _p(residual), int(bool(relu)), _stream())
     _lib.check(rc, "u2pl_conv_bf16_nhwc")
     return out
+
+
+def conv_bf16_nhwc_stats(x, weight, dilation=1):
+    """Raw convolution output (bf16, channels-last) and its per-channel [sum | sum of squares] (fp32 [2, Cout]) from the
+    same kernel pass -- what a train-mode BatchNorm needs before it can normalise (csrc/conv_tc.cu, kStats epilogue)."""
+    _need_cuda(x, weight)
+    lib = _lib.load()
+    N, Cin, H, W = x.shape
+    Cout, k = weight.shape[0], weight.shape[2]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    assert weight.shape[1] == Cin and weight.shape[3] == k and k in (1, 3)
+    wk = weight.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
+    out = torch.empty((N, Cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    parts = int(lib.u2pl_conv_stat_parts(N, H, W, k))
+    part = torch.empty((parts, 2, Cout), dtype=torch.float32, device=x.device)
+    sums = torch.empty((2, Cout), dtype=torch.float32, device=x.device)
+    rc = lib.u2pl_conv_bf16_nhwc_stats(_p(x), _p(wk), _p(out), N, H, W, Cin, Cout, k, int(dilation), _p(part), _p(sums),
+                                       _stream())
+    _lib.check(rc, "u2pl_conv_bf16_nhwc_stats")
+    return out, sums
