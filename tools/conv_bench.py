@@ -22,6 +22,7 @@ SHAPES = [  # name, N, Cin, H, W, Cout, k, d
     ("head 3x3 1280->256", 16, 1280, 65, 65, 256, 3, 1),
     ("decoder 3x3 512->256 @129", 16, 512, 129, 129, 256, 3, 1),
     ("decoder 3x3 256->256 @129", 16, 256, 129, 129, 256, 3, 1),
+    ("8192^3 GEMM as a 1x1 conv (128x256 tile; compare tools/gemm_bench.py: 128x128 tile, cuBLAS)", 1, 8192, 8192, 1, 8192, 1, 1),
 ]
 
 
