@@ -26,3 +26,6 @@ else
   done
 fi
 tail -n 3 $OUT/r2_*.log 2>/dev/null
+# profiling (run separately, after the tests above are green):
+#   gpurun --timeout 600 -- 'ncu --set full --clock-control none --import-source on -k regex:conv_tc -c 1 -o gpurun_out/r02_conv_tc python tools/conv_one.py layer3'
+#   gpurun --timeout 600 -- 'U2PL_TC_CONV=1 U2PL_TC_TRAIN=1 python tools/step_profile.py > gpurun_out/r02_step_profile.txt'
