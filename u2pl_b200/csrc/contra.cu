@@ -19,6 +19,7 @@
 // Feature tensors are addressed through element strides (sn, sd, sp) so both NCHW
 // (sd = h*w, sp = 1) and channels-last (sd = 1, sp = D) layouts are read in place.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 
@@ -530,6 +531,144 @@ infonce_fwd_kernel(InfoNceArgs a)
     if (c1) *reinterpret_cast<float4 *>(g + d1) = make_float4(gv[4], gv[5], gv[6], gv[7]);
 }
 
+// Same kernel with kDepth key rows in flight per warp instead of one (the loop is latency-bound at depth 1: ~1 us per
+// 1 KB row, 51 rows per query).  Arithmetic and its order are unchanged, so results are bit-identical.  Opt-in
+// (U2PL_INFONCE_DEPTH=2|4) until measured.
+template <bool kPeer, int kDepth>
+__global__ void __launch_bounds__(128)
+infonce_fwd_pipelined_kernel(InfoNceArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= a.nact * a.nq) return;
+    const int act = w / a.nq;
+    const int cls = a.act_class[act];
+    // ---- ordinal -> pixel (k-th anchor pixel of class cls in row-major order)
+    const uint32_t k = static_cast<uint32_t>(a.a_ord[w]);
+    const uint32_t *off = a.blockoff_an + static_cast<size_t>(cls) * a.nb;
+    uint32_t lo = 0, hi = a.nb;                            // last block with off[b] <= k
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= k) lo = mid; else hi = mid;
+    }
+    uint32_t kk = k - __ldg(off + lo);
+    const uint32_t base = lo * kBlk + lane * 8;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t pix = base + j;
+        const uint32_t b = pix < a.P ? __ldg(a.an_bits + pix) : 0u;
+        mine |= ((b >> cls) & 1u) << j;
+    }
+    uint32_t inc = __popc(mine);
+    const uint32_t cnt = inc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    const uint32_t excl = inc - cnt;
+    int found = -1;
+    if (kk >= excl && kk < inc) {
+        uint32_t r = kk - excl, m = mine;
+        for (uint32_t t = 0; t < r; ++t) m &= m - 1;
+        found = static_cast<int>(base + __ffs(m) - 1);
+    }
+    const uint32_t who = __ballot_sync(0xffffffffu, found >= 0);
+    const int pix = __shfl_sync(0xffffffffu, found, who ? __ffs(who) - 1 : 0);
+    if (lane == 0) a.anchor_pix[w] = pix;
+    if (pix < 0) { if (lane == 0) a.loss_q[w] = __uint_as_float(0x7fc00000u); return; }   // inconsistent ordinal
+    // ---- anchor row: lane owns channels [4*lane, 4*lane+4) and [128+4*lane, ...)
+    const uint32_t n = static_cast<uint32_t>(pix) / a.hw, p = static_cast<uint32_t>(pix) - n * a.hw;
+    const float *ar = a.rep + static_cast<long long>(n) * a.sn + static_cast<long long>(p) * a.sp;
+    float av[8];
+    const uint32_t d0 = 4 * lane, d1 = 128 + 4 * lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        av[j] = (d0 + j < a.D) ? __ldg(ar + static_cast<long long>(d0 + j) * a.sd) : 0.0f;
+        av[4 + j] = (d1 + j < a.D) ? __ldg(ar + static_cast<long long>(d1 + j) * a.sd) : 0.0f;
+    }
+    float ss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += av[j] * av[j];
+    ss = warp_sum(ss);
+    const float eps = 1e-8f;
+    const float anorm = sqrtf(ss);
+    const float ainv = 1.0f / fmaxf(anorm, eps);           // torch.cosine_similarity: x / max(||x||, eps)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) av[j] *= ainv;
+    // ---- keys: prototype first (:201-207,220-222), then the sampled negatives
+    float m = -INFINITY, s = 0.0f, u = 0.0f, l0 = 0.0f;
+    float V[8], K0[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { V[j] = 0.0f; K0[j] = 0.0f; }
+    const int32_t *rows = a.neg_rows + static_cast<size_t>(w) * a.nneg;
+    const float *bank = kPeer ? a.class_bank[act] : a.bank;
+    const bool c0 = d0 < a.D, c1 = d1 < a.D;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *kr0 = a.proto + static_cast<size_t>(cls) * a.D;
+    // key 0 is the prototype, key k >= 1 is bank row rows[k-1]; q0/q1[i] hold key (t + i) of the current group
+    float4 q0[kDepth], q1[kDepth];
+    q0[0] = c0 ? __ldg(reinterpret_cast<const float4 *>(kr0 + d0)) : z4;
+    q1[0] = c1 ? __ldg(reinterpret_cast<const float4 *>(kr0 + d1)) : z4;
+#pragma unroll
+    for (int i = 1; i < kDepth; ++i) {
+        q0[i] = z4; q1[i] = z4;
+        if (i - 1 < a.nneg) {
+            const float *kn_ = bank + static_cast<size_t>(__ldg(rows + i - 1)) * a.D;
+            q0[i] = c0 ? __ldg(reinterpret_cast<const float4 *>(kn_ + d0)) : z4;
+            q1[i] = c1 ? __ldg(reinterpret_cast<const float4 *>(kn_ + d1)) : z4;
+        }
+    }
+    for (int t = 0; t <= a.nneg; t += kDepth) {
+#pragma unroll
+        for (int i = 0; i < kDepth; ++i) {
+            if (t + i > a.nneg) continue;                      // (uniform across the warp; no `break`: keeps q0/q1 in registers)
+            const float4 x0 = q0[i], x1 = q1[i];
+            const int nxt = t + i + kDepth;                    // key that takes this slot: bank row rows[nxt - 1]
+            if (nxt <= a.nneg) {
+                const float *kn_ = bank + static_cast<size_t>(__ldg(rows + nxt - 1)) * a.D;
+                q0[i] = c0 ? __ldg(reinterpret_cast<const float4 *>(kn_ + d0)) : z4;
+                q1[i] = c1 ? __ldg(reinterpret_cast<const float4 *>(kn_ + d1)) : z4;
+            }
+            float kv[8];
+            kv[0] = x0.x; kv[1] = x0.y; kv[2] = x0.z; kv[3] = x0.w;
+            kv[4] = x1.x; kv[5] = x1.y; kv[6] = x1.z; kv[7] = x1.w;
+            float dot = 0.0f, kn = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { dot += av[j] * kv[j]; kn += kv[j] * kv[j]; }
+            const float2 r2 = warp_sum2(dot, kn);
+            const float kinv = 1.0f / fmaxf(sqrtf(r2.y), eps);
+            const float l = r2.x * kinv;                       // cosine similarity
+            const float z = l * a.inv_temp;
+            const float mn = fmaxf(m, z);
+            const float cs = __expf(m - mn), wgt = __expf(z - mn);
+            s = s * cs + wgt;
+            u = u * cs + wgt * l;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) V[j] = V[j] * cs + wgt * (kv[j] * kinv);
+            m = mn;
+            if (t + i == 0) {
+                l0 = l;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) K0[j] = kv[j] * kinv;
+            }
+        }
+    }
+    const float loss = m + logf(s) - l0 * a.inv_temp;      // CE(logits/temp, 0)  (:228-230)
+    if (lane == 0) a.loss_q[w] = loss;
+    // d CE / d anchor = (1/(temp*||a||)) [ (sum_k p_k k^ - k^_0) - (sum_k p_k l_k - l_0) a^ ]
+    const float sinv = 1.0f / s;
+    const float coef = a.scale * a.inv_temp * ainv;
+    const float proj = (anorm >= eps) ? (u * sinv - l0) : 0.0f;
+    float *g = a.grad_rows + static_cast<size_t>(w) * a.D;
+    float gv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gv[j] = coef * ((V[j] * sinv - K0[j]) - proj * av[j]);
+    if (c0) *reinterpret_cast<float4 *>(g + d0) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    if (c1) *reinterpret_cast<float4 *>(g + d1) = make_float4(gv[4], gv[5], gv[6], gv[7]);
+}
+
 // sum of per-query losses in a fixed order: loss = scale * sum_q CE_q
 __global__ void __launch_bounds__(256)
 infonce_loss_kernel(const float *__restrict__ loss_q, int n, float scale, float *__restrict__ loss)
@@ -675,6 +814,12 @@ extern "C" int u2pl_bank_append(const float *src_rows, float *bank, int64_t D, c
     return check_launch("bank_append");
 }
 
+static int infonce_depth()
+{
+    static const int d = [] { const char *e = getenv("U2PL_INFONCE_DEPTH"); return e ? atoi(e) : 1; }();
+    return d;
+}
+
 extern "C" int u2pl_infonce_forward(const float *rep, int64_t sn, int64_t sd, int64_t sp,
                                     int64_t P, int64_t D, int64_t hw,
                                     const uint32_t *an_bits, const uint32_t *blockoff_an,
@@ -696,7 +841,10 @@ extern "C" int u2pl_infonce_forward(const float *rep, int64_t sn, int64_t sd, in
     a.scale = 1.0f / (static_cast<float>(nq) * static_cast<float>(valid_seg));
     a.loss_q = loss_q; a.grad_rows = grad_rows; a.anchor_pix = anchor_pix;
     const int warps = nact * nq;
-    infonce_fwd_kernel<false><<<(warps + 3) / 4, 128, 0, s>>>(a);
+    const int depth = infonce_depth();
+    if (depth == 4) infonce_fwd_pipelined_kernel<false, 4><<<(warps + 3) / 4, 128, 0, s>>>(a);
+    else if (depth == 2) infonce_fwd_pipelined_kernel<false, 2><<<(warps + 3) / 4, 128, 0, s>>>(a);
+    else infonce_fwd_kernel<false><<<(warps + 3) / 4, 128, 0, s>>>(a);
     infonce_loss_kernel<<<1, 256, 0, s>>>(loss_q, warps, a.scale, loss);
     return check_launch("infonce_forward", 2);
 }
@@ -723,7 +871,10 @@ extern "C" int u2pl_infonce_forward_sharded(const float *rep, int64_t sn, int64_
     a.scale = 1.0f / (static_cast<float>(nq) * static_cast<float>(valid_seg));
     a.loss_q = loss_q; a.grad_rows = grad_rows; a.anchor_pix = anchor_pix;
     const int warps = nact * nq;
-    infonce_fwd_kernel<true><<<(warps + 3) / 4, 128, 0, s>>>(a);
+    const int depth = infonce_depth();
+    if (depth == 4) infonce_fwd_pipelined_kernel<true, 4><<<(warps + 3) / 4, 128, 0, s>>>(a);
+    else if (depth == 2) infonce_fwd_pipelined_kernel<true, 2><<<(warps + 3) / 4, 128, 0, s>>>(a);
+    else infonce_fwd_kernel<true><<<(warps + 3) / 4, 128, 0, s>>>(a);
     infonce_loss_kernel<<<1, 256, 0, s>>>(loss_q, warps, a.scale, loss);
     return check_launch("infonce_forward_sharded", 2);
 }
