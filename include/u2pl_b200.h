@@ -299,6 +299,17 @@ int u2pl_conv_bf16_nhwc_stats(const void *x, const void *wgt, void *out, int64_t
                               int64_t cin, int64_t cout, int ksize, int dilation, float *stat_part, float *sums,
                               void *stream);
 
+/* Weight gradient of the same stride-1 "same" 3x3 (dilated) convolution on the tensor cores, operands read in place
+ * from the channels-last tensors (both are MN-major for this contraction; no transposes, no cropped copies):
+ *   partial[s][r*3+s'][co][ci] = sum over the pixels of K-split s of gout[n,h,w,co] * x[n,h+(r-1)d,w+(s'-1)d,ci]
+ * x [n,h,w,cin], gout [n,h,w,cout] bf16 dense; partial fp32 [u2pl_conv_wgrad_splits(...)][9][cout][cin] -- the caller
+ * sums over the first axis and permutes to the weight layout.  cin % 8 == 0, cout % 8 == 0.
+ * replaces: the weight-gradient half of convolution_backward for conv3x3 (resnet.py:25-36), ASPP (base.py:38-75) and
+ * decoder convs (decoder.py:60-113) in loss.backward() (train_semi.py:527). */
+int u2pl_conv_wgrad_splits(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout);
+int u2pl_conv_wgrad_bf16_nhwc(const void *x, const void *gout, float *partial, int64_t n, int64_t h, int64_t w,
+                              int64_t cin, int64_t cout, int dilation, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,3 +82,54 @@ def test_conv_addressing_model(N, Cin, H, W, Cout, k, d):
     ref = F.conv2d(x, w, None, 1, d * (k // 2), d).permute(0, 2, 3, 1).numpy()
     got = conv_model(x.permute(0, 2, 3, 1).contiguous().numpy(), w.permute(0, 2, 3, 1).contiguous().numpy(), k, d, flat=(k == 1))
     assert np.abs(got - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
+
+
+# ------------------------------------------------------------------ csrc/wgrad_tc.cu addressing
+def _patch(t, c0, nch, w0, h0, n):
+    """4-D TMA box {64 channels, 16 w, 4 h, 1 image} of an NHWC tensor at signed coordinates -> [64 pixels, nch]."""
+    N, H, W, C = t.shape
+    out = np.zeros((4, 16, nch), np.float32)
+    for i in range(4):
+        for j in range(16):
+            h, w = h0 + i, w0 + j
+            if 0 <= h < H and 0 <= w < W and c0 < C:
+                c1 = min(c0 + nch, C)
+                out[i, j, :c1 - c0] = t[n, h, w, c0:c1]
+    return out.reshape(64, nch)
+
+
+def wgrad_model(x_nhwc, g_nhwc, dil, splits):
+    N, H, W, Cin = x_nhwc.shape
+    Cout = g_nhwc.shape[3]
+    tiles_h, tiles_w = (H + 3) // 4, (W + 15) // 16
+    kb_total = N * tiles_h * tiles_w
+    part = np.zeros((splits, 9, Cout, Cin), np.float32)
+    for sp in range(splits):
+        lo, hi = kb_total * sp // splits, kb_total * (sp + 1) // splits
+        assert hi > lo
+        for tap in range(9):
+            dh, dw = (tap // 3 - 1) * dil, (tap % 3 - 1) * dil
+            for co0 in range(0, Cout, 128):
+                for ci0 in range(0, Cin, 256):
+                    acc = np.zeros((128, 256), np.float32)
+                    for kb in range(lo, hi):
+                        img, rem = divmod(kb, tiles_h * tiles_w)
+                        h0, w0 = (rem // tiles_w) * 4, (rem % tiles_w) * 16
+                        a = _patch(g_nhwc, co0, 128, w0, h0, img)                 # [64 pix, 128 co]
+                        b = _patch(x_nhwc, ci0, 256, w0 + dw, h0 + dh, img)       # [64 pix, 256 ci]
+                        acc += a.T @ b
+                    r1, c1 = min(128, Cout - co0), min(256, Cin - ci0)
+                    part[sp, tap, co0:co0 + r1, ci0:ci0 + c1] = acc[:r1, :c1]
+    return part.sum(0).reshape(3, 3, Cout, Cin).transpose(2, 3, 0, 1)
+
+
+@pytest.mark.parametrize("N,Cin,H,W,Cout,d,splits", [(2, 24, 9, 19, 16, 1, 1), (1, 264, 7, 17, 136, 2, 3), (2, 8, 11, 5, 8, 5, 2)])
+def test_wgrad_addressing_model(N, Cin, H, W, Cout, d, splits):
+    g = torch.Generator().manual_seed(Cin + d)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g, requires_grad=True)
+    y = F.conv2d(x, w, None, 1, d, d)
+    go = torch.randn(y.shape, generator=g)
+    y.backward(go)
+    got = wgrad_model(x.permute(0, 2, 3, 1).contiguous().numpy(), go.permute(0, 2, 3, 1).contiguous().numpy(), d, splits)
+    assert np.abs(got - w.grad.numpy()).max() <= 2e-4 * max(1.0, float(w.grad.abs().max()))

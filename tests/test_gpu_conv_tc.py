@@ -154,3 +154,20 @@ def test_train_mode_model_with_tc_train_matches_default():
         assert (ga - gb).norm() <= 0.08 * ga.norm(), name
     ra, rb = res[0][2]["encoder.layer2.1.bn2.running_var"], res[1][2]["encoder.layer2.1.bn2.running_var"]
     assert (ra - rb).abs().max() <= 0.02 * ra.abs().max().item()
+
+
+@pytest.mark.skipif(os.environ.get("U2PL_TC_WGRAD", "0") != "1", reason="run tools/umma_probe_sweep.sh first, then set U2PL_TC_WGRAD=1")
+@pytest.mark.parametrize("N,Cin,H,W,Cout,d", [(2, 256, 65, 65, 256, 2), (2, 2048, 33, 35, 256, 12), (1, 72, 20, 24, 40, 3),
+                                              (3, 512, 17, 19, 512, 4)])
+def test_wgrad_tc_matches_torch(N, Cin, H, W, Cout, d):
+    """csrc/wgrad_tc.cu (MN-major tcgen05 operands read in place) against autograd's weight gradient in fp32."""
+    from u2pl_b200 import ops
+    torch.manual_seed(Cin + d)
+    x = _cl(torch.randn(N, Cin, H, W, device="cuda").bfloat16())
+    g = _cl(torch.randn(N, Cout, H, W, device="cuda").bfloat16())
+    got = ops.conv_wgrad_bf16_nhwc(x, g, d)
+    w = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
+    torch.backends.cudnn.allow_tf32 = False
+    F.conv2d(x.float(), w, None, 1, d, d).backward(g.float())
+    assert got.shape == w.grad.shape
+    assert (got - w.grad).abs().max() <= 2e-3 * max(1.0, w.grad.abs().max().item())        # fp32 accumulation both sides

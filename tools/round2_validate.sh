@@ -14,6 +14,8 @@ if [ "${1:-1}" = "1" ]; then
   timeout 300 python bench.py --steps 10 --warmup 3                                 > $OUT/r2_bench_n1.json 2>$OUT/r2_bench_n1.err;       echo "bench ours: $?"
   U2PL_TC_CONV=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_tcconv.json 2>$OUT/r2_bench_n1_tcconv.err; echo "bench ours+tc_conv: $?"
   U2PL_TC_CONV=1 U2PL_TC_TRAIN=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_tctrain.json 2>$OUT/r2_bench_n1_tctrain.err; echo "bench ours+tc_conv+tc_train: $?"
+  timeout 200 bash tools/umma_probe_sweep.sh > $OUT/r2_umma_probe.txt 2>&1; echo "umma MN-major probe: $? (0 = expected descriptor encoding confirmed)"
+  U2PL_TC_CONV=1 U2PL_TC_WGRAD=1 timeout 300 python -m pytest tests/test_gpu_conv_tc.py -q -k wgrad > $OUT/r2_pytest_wgrad_tc.log 2>&1; echo "pytest wgrad_tc: $?"
   for d in 1 2 4; do
     U2PL_INFONCE_DEPTH=$d timeout 120 python tools/contra_bench.py > $OUT/r2_contra_bench_depth$d.log 2>&1; echo "contra_bench depth $d: $?"
   done

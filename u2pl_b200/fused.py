@@ -35,7 +35,8 @@ import os
 # transposed weight); weight gradients stay with cuDNN / the GEMM paths above.  Same status.
 ENABLED = {"bn": True, "wgrad": True, "tc_conv": os.environ.get("U2PL_TC_CONV", "0") == "1",
            "wgrad_stack": os.environ.get("U2PL_WGRAD_STACK", "0") == "1",
-           "tc_train": os.environ.get("U2PL_TC_TRAIN", "0") == "1"}
+           "tc_train": os.environ.get("U2PL_TC_TRAIN", "0") == "1",
+           "tc_wgrad": os.environ.get("U2PL_TC_WGRAD", "0") == "1"}   # 3x3 stride-1 weight gradients via csrc/wgrad_tc.cu
 
 
 def _world():
@@ -167,7 +168,10 @@ class _ConvTCFn(torch.autograd.Function):
         gout = gout.contiguous(memory_format=torch.channels_last)
         dx = conv_bf16_nhwc(gout, dgrad_weight(w), d) if ctx.needs_input_grad[0] else None
         dw = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and ENABLED["tc_wgrad"] and k == 3:
+            from .ops import conv_wgrad_bf16_nhwc
+            dw = conv_wgrad_bf16_nhwc(x, gout, d).to(w.dtype)
+        elif ctx.needs_input_grad[1]:
             pad = d * (k // 2)
             dw = torch.ops.aten.convolution_backward(gout, x, w, None, [1, 1], [pad, pad], [d, d], False, [0, 0], 1,
                                                      [False, True, False])[1]
@@ -280,6 +284,9 @@ class _DilatedConvFn(torch.autograd.Function):
                 hi = min(n_out - 1, (n_in - 1 - off) // s)
                 return lo, hi, off
 
+            if s == 1 and ENABLED["tc_wgrad"] and _is_cl_bf16(x) and _is_cl_bf16(gout):
+                from .ops import conv_wgrad_bf16_nhwc
+                return dx, conv_wgrad_bf16_nhwc(x, gout, d).to(w.dtype), None, None
             if s == 1 and ENABLED["wgrad_stack"]:
                 # dw[co,ky,kx,ci] = sum_q g9[q, (ky,kx), co] * x[q, ci] with g9[q, tap] = g[q - offset(tap)] (zero where
                 # that falls outside the map): x is read in place, only the Co-channel gradient is copied (9 shifted times)

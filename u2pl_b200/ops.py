@@ -322,3 +322,21 @@ def conv_bf16_nhwc_stats(x, weight, dilation=1):
                                        _stream())
     _lib.check(rc, "u2pl_conv_bf16_nhwc_stats")
     return out, sums
+
+
+def conv_wgrad_bf16_nhwc(x, gout, dilation=1):
+    """Weight gradient [Cout, Cin, 3, 3] (fp32) of a stride-1 "same" 3x3 convolution from the channels-last bf16 input
+    and output gradient, on the tensor cores with MN-major operands read in place (csrc/wgrad_tc.cu)."""
+    _need_cuda(x, gout)
+    lib = _lib.load()
+    N, Cin, H, W = x.shape
+    Cout = gout.shape[1]
+    assert gout.shape == (N, Cout, H, W)
+    for t in (x, gout):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous(memory_format=torch.channels_last)
+    splits = int(lib.u2pl_conv_wgrad_splits(N, H, W, Cin, Cout))
+    part = torch.empty((splits, 9, Cout, Cin), dtype=torch.float32, device=x.device)
+    rc = lib.u2pl_conv_wgrad_bf16_nhwc(_p(x), _p(gout), _p(part), N, H, W, Cin, Cout, int(dilation), _stream())
+    _lib.check(rc, "u2pl_conv_wgrad_bf16_nhwc")
+    dw = part.sum(0) if splits > 1 else part[0]
+    return dw.view(3, 3, Cout, Cin).permute(2, 3, 0, 1)
