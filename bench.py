@@ -215,6 +215,8 @@ def eager_arm(args, dev=None):
         return {k: v.detach().to(dev).requires_grad_(v.requires_grad) for k, v in base.items()}
 
     while True:
+        if on_gpu:
+            torch.cuda.empty_cache()                          # (after an OOM retry: the failed attempt's frames are gone here)
         try:
             ref = eager_step.EagerStep(on_dev(), on_dev(), cfg, arch)
             g = torch.Generator().manual_seed(7)
@@ -247,8 +249,7 @@ def eager_arm(args, dev=None):
         except torch.cuda.OutOfMemoryError:
             if bl == 1:
                 raise
-            del ref
-            torch.cuda.empty_cache()
+            ref = None
             bl, bu = bl // 2, bu // 2
     value = (bl + bu) / (ms * 1e-3)
     h2d = image_l.numel() * 4 + label_l.numel() * 8 + image_u.numel() * 4
