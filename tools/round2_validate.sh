@@ -35,3 +35,5 @@ tail -n 3 $OUT/r2_*.log 2>/dev/null
 # profiling (run separately, after the tests above are green):
 #   gpurun --timeout 600 -- 'ncu --set full --clock-control none --import-source on -k regex:conv_tc -c 1 -o gpurun_out/r02_conv_tc python tools/conv_one.py layer3'
 #   gpurun --timeout 600 -- 'U2PL_TC_CONV=1 U2PL_TC_TRAIN=1 python tools/step_profile.py > gpurun_out/r02_step_profile.txt'
+#   full ncu launch list of one bench step (≈ 20 GPU-min for ~6000 launches; round 1's attempt was cut at 2517 launches):
+#   gpurun --timeout 1500 -- 'U2PL_BENCH_FAST=1 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_bench_step_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r02_bench_under_ncu.log 2>&1'
