@@ -1,8 +1,9 @@
 """GPU: tcgen05 implicit-GEMM convolution (csrc/conv_tc.cu, `u2pl_conv_bf16_nhwc`) against F.conv2d in fp32 on the
 same bf16-representable inputs; tolerance = bf16 rounding of the output (1e-2 relative to the output scale).
 
-OPT-IN (U2PL_TC_CONV=1): this kernel was written after round 1's GPU minutes were spent and has not executed on a
-B200 yet, so it is neither on the default path (fused.ENABLED["tc_conv"]) nor in the default GPU suite.  First GPU
+OPT-IN (U2PL_TC_CONV=1): written after round 1's GPU minutes were spent.  The kernels matched CPU loops on a B200 in
+the torch-free self-test (tools/cu/tc_selftest.cu, profiles/r01_tc_selftest.txt); these tests -- the layer shapes of
+the network and the Python routing -- have not run yet, so the path is neither default nor in the default GPU suite.  First GPU
 call of the next round: `U2PL_TC_CONV=1 python -m pytest tests/test_gpu_conv_tc.py -x -q`."""
 import os
 

@@ -1,0 +1,198 @@
+// tc_selftest.cu -- torch-free check of the tensor-core entry points of libu2pl_b200.so through the C ABI:
+// u2pl_conv_bf16_nhwc (plain / epilogue / statistics) and u2pl_conv_wgrad_bf16_nhwc against CPU loops.
+// Starts in about a second (no Python, no torch import), so it fits in the smallest GPU slot:
+//   nvcc -O2 -std=c++17 -o tools/cu/tc_selftest.bin tools/cu/tc_selftest.cu -ldl     (built here, runs on the box)
+//   ./tools/cu/tc_selftest.bin [conv|stats|wgrad|all]
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <vector>
+#include <cuda_runtime.h>
+
+typedef int (*conv_fn)(const void *, const void *, void *, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float *,
+                       const float *, const void *, int, void *);
+typedef int (*conv_stats_fn)(const void *, const void *, void *, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, float *, float *, void *);
+typedef int64_t (*parts_fn)(int64_t, int64_t, int64_t, int);
+typedef int (*splits_fn)(int64_t, int64_t, int64_t, int64_t, int64_t);
+typedef int (*wgrad_fn)(const void *, const void *, float *, int64_t, int64_t, int64_t, int64_t, int64_t, int, void *);
+typedef const char *(*err_fn)(void);
+
+static uint16_t f2bf(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return static_cast<uint16_t>(u >> 16);
+}
+static float bf2f(uint16_t h)
+{
+    uint32_t u = static_cast<uint32_t>(h) << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+static uint32_t g_seed = 777u;
+static float rnd() { g_seed = g_seed * 1664525u + 1013904223u; return (static_cast<int>((g_seed >> 20) % 2001) - 1000) / 1000.0f; }
+
+template <typename T> static T *to_dev(const std::vector<T> &h)
+{
+    T *d = nullptr;
+    cudaMalloc(&d, h.size() * sizeof(T));
+    cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+}
+
+struct Lib { conv_fn conv; conv_stats_fn conv_stats; parts_fn parts; splits_fn splits; wgrad_fn wgrad; err_fn err; };
+
+static int check_conv(const Lib &L, int N, int Cin, int H, int W, int Cout, int k, int d, bool epi, bool stats)
+{
+    const size_t nx = static_cast<size_t>(N) * H * W * Cin, nw = static_cast<size_t>(Cout) * k * k * Cin, ny = static_cast<size_t>(N) * H * W * Cout;
+    std::vector<uint16_t> x(nx), w(nw), res(ny);
+    std::vector<float> scale(Cout), shift(Cout);
+    for (auto &v : x) v = f2bf(rnd());
+    for (auto &v : w) v = f2bf(rnd() / sqrtf(static_cast<float>(Cin * k * k)) * 3.0f);
+    for (auto &v : res) v = f2bf(rnd());
+    for (int c = 0; c < Cout; ++c) { scale[c] = 1.0f + 0.5f * rnd(); shift[c] = rnd(); }
+    std::vector<float> ref(ny);
+    const int pad = d * (k / 2);
+    for (int n = 0; n < N; ++n)
+        for (int h = 0; h < H; ++h)
+            for (int ww = 0; ww < W; ++ww)
+                for (int co = 0; co < Cout; ++co) {
+                    float acc = 0.0f;
+                    for (int r = 0; r < k; ++r)
+                        for (int s = 0; s < k; ++s) {
+                            const int hi = h + r * d - pad, wi = ww + s * d - pad;
+                            if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+                            const uint16_t *xp = &x[((static_cast<size_t>(n) * H + hi) * W + wi) * Cin];
+                            const uint16_t *wp = &w[((static_cast<size_t>(co) * k + r) * k + s) * Cin];
+                            for (int ci = 0; ci < Cin; ++ci) acc += bf2f(xp[ci]) * bf2f(wp[ci]);
+                        }
+                    const size_t o = ((static_cast<size_t>(n) * H + h) * W + ww) * Cout + co;
+                    if (epi) { acc = acc * scale[co] + shift[co] + bf2f(res[o]); acc = acc > 0.0f ? acc : 0.0f; }
+                    ref[o] = acc;
+                }
+    uint16_t *dx = to_dev(x), *dw = to_dev(w), *dres = to_dev(res), *dy = nullptr;
+    float *dscale = to_dev(scale), *dshift = to_dev(shift);
+    cudaMalloc(&dy, ny * 2);
+    cudaMemset(dy, 0xff, ny * 2);
+    int rc;
+    std::vector<float> sums(2 * Cout, 0.0f);
+    if (stats) {
+        const int64_t parts = L.parts(N, H, W, k);
+        float *dpart = nullptr, *dsums = nullptr;
+        cudaMalloc(&dpart, parts * 2 * Cout * 4);
+        cudaMalloc(&dsums, 2 * Cout * 4);
+        rc = L.conv_stats(dx, dw, dy, N, H, W, Cin, Cout, k, d, dpart, dsums, nullptr);
+        cudaDeviceSynchronize();
+        cudaMemcpy(sums.data(), dsums, 2 * Cout * 4, cudaMemcpyDeviceToHost);
+    } else {
+        rc = L.conv(dx, dw, dy, N, H, W, Cin, Cout, k, d, epi ? dscale : nullptr, epi ? dshift : nullptr, epi ? dres : nullptr, epi ? 1 : 0, nullptr);
+    }
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (rc != 0 || e != cudaSuccess) {
+        printf("conv N=%d Cin=%d %dx%d Cout=%d k=%d d=%d epi=%d stats=%d: rc=%d cuda=%s err=%s\n", N, Cin, H, W, Cout, k, d, epi, stats, rc,
+               cudaGetErrorString(e), L.err());
+        return 1;
+    }
+    std::vector<uint16_t> y(ny);
+    cudaMemcpy(y.data(), dy, ny * 2, cudaMemcpyDeviceToHost);
+    float worst = 0.0f, scale_ref = 1.0f;
+    for (size_t i = 0; i < ny; ++i) scale_ref = fmaxf(scale_ref, fabsf(ref[i]));
+    size_t bad = 0;
+    for (size_t i = 0; i < ny; ++i) {
+        const float dlt = fabsf(bf2f(y[i]) - ref[i]);
+        if (!(dlt <= 1e-2f * scale_ref)) ++bad;
+        if (dlt > worst || dlt != dlt) worst = dlt;
+    }
+    double s_err = 0.0;
+    if (stats) {
+        for (int c = 0; c < Cout; ++c) {
+            double a = 0.0, b = 0.0;
+            for (size_t p = 0; p < static_cast<size_t>(N) * H * W; ++p) { const double v = bf2f(y[p * Cout + c]); a += v; b += v * v; }
+            s_err = fmax(s_err, fabs(a - sums[c]) / (1.0 + fabs(a)));
+            s_err = fmax(s_err, fabs(b - sums[Cout + c]) / (1.0 + fabs(b)));
+        }
+        if (s_err > 1e-3) ++bad;
+    }
+    printf("conv N=%d Cin=%d %dx%d Cout=%d k=%d d=%d epi=%d stats=%d: mismatches=%zu/%zu max_err=%g (ref max %g) stats_rel_err=%g  %s\n", N, Cin,
+           H, W, Cout, k, d, epi, stats, bad, ny, worst, scale_ref, s_err, bad == 0 ? "OK" : "WRONG");
+    return bad == 0 ? 0 : 1;
+}
+
+static int check_wgrad(const Lib &L, int N, int Cin, int H, int W, int Cout, int d)
+{
+    const size_t nx = static_cast<size_t>(N) * H * W * Cin, ng = static_cast<size_t>(N) * H * W * Cout, nd = static_cast<size_t>(9) * Cout * Cin;
+    std::vector<uint16_t> x(nx), g(ng);
+    for (auto &v : x) v = f2bf(rnd());
+    for (auto &v : g) v = f2bf(rnd());
+    std::vector<float> ref(nd, 0.0f);
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dh = (tap / 3 - 1) * d, dw = (tap % 3 - 1) * d;
+        for (int n = 0; n < N; ++n)
+            for (int h = 0; h < H; ++h)
+                for (int w = 0; w < W; ++w) {
+                    const int hi = h + dh, wi = w + dw;
+                    if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+                    const uint16_t *gp = &g[((static_cast<size_t>(n) * H + h) * W + w) * Cout];
+                    const uint16_t *xp = &x[((static_cast<size_t>(n) * H + hi) * W + wi) * Cin];
+                    for (int co = 0; co < Cout; ++co) {
+                        const float gv = bf2f(gp[co]);
+                        float *row = &ref[(static_cast<size_t>(tap) * Cout + co) * Cin];
+                        for (int ci = 0; ci < Cin; ++ci) row[ci] += gv * bf2f(xp[ci]);
+                    }
+                }
+    }
+    const int splits = L.splits(N, H, W, Cin, Cout);
+    uint16_t *dx = to_dev(x), *dg = to_dev(g);
+    float *dpart = nullptr;
+    cudaMalloc(&dpart, static_cast<size_t>(splits) * nd * 4);
+    cudaMemset(dpart, 0xff, static_cast<size_t>(splits) * nd * 4);
+    const int rc = L.wgrad(dx, dg, dpart, N, H, W, Cin, Cout, d, nullptr);
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (rc != 0 || e != cudaSuccess) { printf("wgrad: rc=%d cuda=%s err=%s\n", rc, cudaGetErrorString(e), L.err()); return 1; }
+    std::vector<float> part(static_cast<size_t>(splits) * nd);
+    cudaMemcpy(part.data(), dpart, part.size() * 4, cudaMemcpyDeviceToHost);
+    float worst = 0.0f, mx = 1.0f;
+    size_t bad = 0;
+    for (size_t i = 0; i < nd; ++i) {
+        float a = 0.0f;
+        for (int s = 0; s < splits; ++s) a += part[s * nd + i];
+        const float dlt = fabsf(a - ref[i]);
+        mx = fmaxf(mx, fabsf(ref[i]));
+        if (!(dlt <= 2e-3f * fmaxf(1.0f, fabsf(ref[i])) + 1e-2f)) ++bad;
+        if (dlt > worst || dlt != dlt) worst = dlt;
+    }
+    printf("wgrad N=%d Cin=%d %dx%d Cout=%d d=%d splits=%d: mismatches=%zu/%zu max_err=%g (ref max %g)  %s\n", N, Cin, H, W, Cout, d, splits, bad,
+           nd, worst, mx, bad == 0 ? "OK" : "WRONG");
+    return bad == 0 ? 0 : 1;
+}
+
+int main(int argc, char **argv)
+{
+    const char *what = argc > 1 ? argv[1] : "all";
+    void *h = dlopen("u2pl_b200/libu2pl_b200.so", RTLD_NOW);
+    if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
+    Lib L;
+    L.conv = reinterpret_cast<conv_fn>(dlsym(h, "u2pl_conv_bf16_nhwc"));
+    L.conv_stats = reinterpret_cast<conv_stats_fn>(dlsym(h, "u2pl_conv_bf16_nhwc_stats"));
+    L.parts = reinterpret_cast<parts_fn>(dlsym(h, "u2pl_conv_stat_parts"));
+    L.splits = reinterpret_cast<splits_fn>(dlsym(h, "u2pl_conv_wgrad_splits"));
+    L.wgrad = reinterpret_cast<wgrad_fn>(dlsym(h, "u2pl_conv_wgrad_bf16_nhwc"));
+    L.err = reinterpret_cast<err_fn>(dlsym(h, "u2pl_last_error"));
+    if (!L.conv || !L.conv_stats || !L.parts || !L.splits || !L.wgrad || !L.err) { fprintf(stderr, "missing symbol\n"); return 2; }
+    int fails = 0;
+    const bool all = !strcmp(what, "all");
+    if (all || !strcmp(what, "conv")) {
+        fails += check_conv(L, 1, 64, 13, 11, 136, 1, 1, false, false);      // flat 1x1, 256-wide channel tile, partial tiles
+        fails += check_conv(L, 1, 72, 20, 24, 40, 3, 3, true, false);        // Cin % 64 != 0, epilogue, 128-wide tile
+        fails += check_conv(L, 2, 128, 17, 33, 256, 3, 2, true, false);      // two K blocks per tap, 256-wide tile
+    }
+    if (all || !strcmp(what, "stats")) fails += check_conv(L, 2, 64, 17, 19, 128, 3, 1, false, true);
+    if (all || !strcmp(what, "wgrad")) fails += check_wgrad(L, 1, 264, 7, 17, 136, 2);
+    printf("%s\n", fails ? "SELFTEST FAILED" : "SELFTEST PASSED");
+    return fails ? 1 : 0;
+}

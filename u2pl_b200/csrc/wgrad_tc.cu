@@ -16,8 +16,8 @@
 // caller.  CTA layout / barriers / persistent loop / two 256-column TMEM stages: as conv_tc.cu.
 //
 // replaces: the weight-gradient half of torch.ops.aten.convolution_backward (cuDNN) for conv3x3 (resnet.py:25-36),
-// the ASPP branches (base.py:38-75) and the decoder convs (decoder.py:60-113).  STATUS: written without GPU access;
-// opt-in (U2PL_TC_WGRAD=1), not on any default path.
+// the ASPP branches (base.py:38-75) and the decoder convs (decoder.py:60-113).  STATUS: matches a CPU loop on a B200 (tools/cu/tc_selftest.cu,
+// profiles/r01_tc_selftest.txt); untimed; opt-in (U2PL_TC_WGRAD=1), not on any default path.
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>

@@ -27,7 +27,8 @@ from .ops import _p, _stream
 import os
 
 # "tc_conv": eval-mode conv + BN (+residual, +ReLU) through the tcgen05 implicit-GEMM kernel (csrc/conv_tc.cu).
-# Off unless U2PL_TC_CONV=1: the kernel was written after round 1's GPU minutes were spent and has not run on a B200 yet.
+# Off unless U2PL_TC_CONV=1: written after round 1's GPU minutes were spent; correct on a B200 in the torch-free self-test
+# (profiles/r01_tc_selftest.txt), but untimed, and this Python routing has not executed on a GPU yet.
 # "wgrad_stack": stride-1 dilated weight gradient as ONE GEMM against nine shifted, zero-padded copies of the (small)
 # output gradient instead of nine GEMMs over cropped copies of the (large) input.  Same status: opt-in, unmeasured.
 # "tc_train": train-mode forward AND data gradient of every eligible stride-1 convolution through the same kernel
