@@ -2,7 +2,7 @@
 // u2pl_conv_bf16_nhwc (plain / epilogue / statistics) and u2pl_conv_wgrad_bf16_nhwc against CPU loops.
 // Starts in about a second (no Python, no torch import), so it fits in the smallest GPU slot:
 //   nvcc -O2 -std=c++17 -o tools/cu/tc_selftest.bin tools/cu/tc_selftest.cu -ldl     (built here, runs on the box)
-//   ./tools/cu/tc_selftest.bin [conv|stats|wgrad|all]
+//   ./tools/cu/tc_selftest.bin [conv|stats|wgrad|all|perf]      (perf: CUDA-event timings at the network's layer shapes)
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -171,6 +171,63 @@ static int check_wgrad(const Lib &L, int N, int Cin, int H, int W, int Cout, int
     return bad == 0 ? 0 : 1;
 }
 
+// ---- timings at the network's layer shapes (T1 batch: 16 images), no CPU reference: TFLOP/s per kernel
+static uint16_t *dev_pattern(size_t n)
+{
+    std::vector<uint16_t> h(1 << 20);
+    for (auto &v : h) v = f2bf(rnd());
+    uint16_t *d = nullptr;
+    cudaMalloc(&d, n * 2);
+    for (size_t o = 0; o < n; o += h.size())
+        cudaMemcpy(d + o, h.data(), (n - o < h.size() ? n - o : h.size()) * 2, cudaMemcpyHostToDevice);
+    return d;
+}
+
+static void perf(const Lib &L)
+{
+    struct Shape { const char *name; int N, Cin, H, W, Cout, k, d; };
+    const Shape shapes[] = {{"layer3.conv1 1x1 1024->256", 16, 1024, 65, 65, 256, 1, 1}, {"layer3.conv2 3x3 d2 256->256", 16, 256, 65, 65, 256, 3, 2},
+                            {"layer3.conv3 1x1 256->1024", 16, 256, 65, 65, 1024, 1, 1}, {"layer4.conv2 3x3 d8 512->512", 16, 512, 65, 65, 512, 3, 8},
+                            {"aspp 3x3 d12 2048->256", 16, 2048, 65, 65, 256, 3, 12}, {"head 3x3 1280->256", 16, 1280, 65, 65, 256, 3, 1},
+                            {"decoder 3x3 256->256 @129", 16, 256, 129, 129, 256, 3, 1}, {"8192^3 as 1x1", 1, 8192, 8192, 1, 8192, 1, 1}};
+    for (const Shape &sh : shapes) {
+        const size_t nx = static_cast<size_t>(sh.N) * sh.H * sh.W * sh.Cin, ny = static_cast<size_t>(sh.N) * sh.H * sh.W * sh.Cout;
+        const size_t nw = static_cast<size_t>(sh.Cout) * sh.k * sh.k * sh.Cin;
+        uint16_t *x = dev_pattern(nx), *w = dev_pattern(nw), *y = dev_pattern(ny);
+        std::vector<float> ones(sh.Cout, 1.0f);
+        float *sc = to_dev(ones), *sf = to_dev(ones);
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        auto time_it = [&](auto fn) {
+            for (int i = 0; i < 3; ++i) fn();
+            cudaEventRecord(a);
+            for (int i = 0; i < 10; ++i) fn();
+            cudaEventRecord(b);
+            cudaEventSynchronize(b);
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, a, b);
+            return ms / 10.0f;
+        };
+        const double flop = 2.0 * sh.N * sh.H * sh.W * static_cast<double>(sh.Cout) * sh.Cin * sh.k * sh.k;
+        const float t_conv = time_it([&] { L.conv(x, w, y, sh.N, sh.H, sh.W, sh.Cin, sh.Cout, sh.k, sh.d, sc, sf, nullptr, 1, nullptr); });
+        printf("perf %-30s conv+bn+relu %8.3f ms %7.1f TFLOP/s", sh.name, t_conv, flop / t_conv / 1e9);
+        if (sh.k == 3) {
+            const int64_t parts = L.parts(sh.N, sh.H, sh.W, sh.k);
+            float *part = nullptr, *sums = nullptr, *wpart = nullptr;
+            cudaMalloc(&part, parts * 2 * sh.Cout * 4); cudaMalloc(&sums, 2 * sh.Cout * 4);
+            const float t_st = time_it([&] { L.conv_stats(x, w, y, sh.N, sh.H, sh.W, sh.Cin, sh.Cout, sh.k, sh.d, part, sums, nullptr); });
+            const int splits = L.splits(sh.N, sh.H, sh.W, sh.Cin, sh.Cout);
+            cudaMalloc(&wpart, static_cast<size_t>(splits) * 9 * sh.Cout * sh.Cin * 4);
+            const float t_wg = time_it([&] { L.wgrad(x, y, wpart, sh.N, sh.H, sh.W, sh.Cin, sh.Cout, sh.d, nullptr); });
+            printf(" | conv+stats %8.3f ms | wgrad (splits %d) %8.3f ms %7.1f TFLOP/s", t_st, splits, t_wg, flop / t_wg / 1e9);
+            cudaFree(part); cudaFree(sums); cudaFree(wpart);
+        }
+        const cudaError_t e = cudaDeviceSynchronize();
+        printf("%s\n", e == cudaSuccess ? "" : cudaGetErrorString(e));
+        cudaFree(x); cudaFree(w); cudaFree(y); cudaFree(sc); cudaFree(sf);
+    }
+}
+
 int main(int argc, char **argv)
 {
     const char *what = argc > 1 ? argv[1] : "all";
@@ -193,6 +250,7 @@ int main(int argc, char **argv)
     }
     if (all || !strcmp(what, "stats")) fails += check_conv(L, 2, 64, 17, 19, 128, 3, 1, false, true);
     if (all || !strcmp(what, "wgrad")) fails += check_wgrad(L, 1, 264, 7, 17, 136, 2);
+    if (!strcmp(what, "perf")) { perf(L); return 0; }
     printf("%s\n", fails ? "SELFTEST FAILED" : "SELFTEST PASSED");
     return fails ? 1 : 0;
 }

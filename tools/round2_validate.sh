@@ -7,6 +7,11 @@ set -u
 mkdir -p gpurun_out
 OUT=gpurun_out
 if [ "${1:-1}" = "1" ]; then
+  # torch-free, seconds: correctness + CUDA-event timings of the tensor-core kernels (run tools/build_selftest.sh first, here)
+  if [ -x tools/cu/tc_selftest.bin ]; then
+    timeout 120 ./tools/cu/tc_selftest.bin all  > $OUT/r2_tc_selftest.txt 2>&1; echo "tc_selftest: $?"
+    timeout 120 ./tools/cu/tc_selftest.bin perf > $OUT/r2_tc_selftest_perf.txt 2>&1; echo "tc_selftest perf: $?"
+  fi
   timeout 600 python -m pytest tests -m gpu -x -q                                   > $OUT/r2_pytest_gpu.log 2>&1;      echo "pytest default: $?"
   U2PL_TC_CONV=1 timeout 300 python -m pytest tests/test_gpu_conv_tc.py -q          > $OUT/r2_pytest_conv_tc.log 2>&1;  echo "pytest conv_tc: $?"
   timeout 200 python tools/conv_bench.py                                            > $OUT/r2_conv_bench.jsonl 2>$OUT/r2_conv_bench.err; echo "conv_bench: $?"
