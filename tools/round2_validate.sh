@@ -11,6 +11,7 @@ if [ "${1:-1}" = "1" ]; then
   if [ -x tools/cu/tc_selftest.bin ]; then
     timeout 120 ./tools/cu/tc_selftest.bin all  > $OUT/r2_tc_selftest.txt 2>&1; echo "tc_selftest: $?"
     timeout 120 ./tools/cu/tc_selftest.bin perf > $OUT/r2_tc_selftest_perf.txt 2>&1; echo "tc_selftest perf: $?"
+    timeout 20 ./tools/cu/umma_2cta_probe.bin   > $OUT/r2_umma_2cta_probe.txt 2>&1; echo "2-CTA probe: $? (124 = hang: protocol error)"
   fi
   timeout 600 python -m pytest tests -m gpu -x -q                                   > $OUT/r2_pytest_gpu.log 2>&1;      echo "pytest default: $?"
   U2PL_TC_CONV=1 timeout 300 python -m pytest tests/test_gpu_conv_tc.py -q          > $OUT/r2_pytest_conv_tc.log 2>&1;  echo "pytest conv_tc: $?"
