@@ -1,0 +1,295 @@
+"""CPU: the PYTHON GLUE around the tensor-core entry points (u2pl_b200/ops.py conv_bf16_nhwc / conv_bf16_nhwc_stats /
+conv_wgrad_bf16_nhwc, fused.conv_bn_act's eval path, fused._ConvTCFn forward / data gradient / weight gradient) with
+the C ABI EMULATED in the test: a fake library object receives the same raw pointers and integer arguments the real
+libu2pl_b200.so would, reinterprets the host memory exactly as the header documents it (x [n,h,w,cin], weight
+[cout,k,k,cin], out [n,h,w,cout], partial [splits,9,cout,cin] ...) and computes with torch.  The kernels themselves are
+checked against CPU loops on the GPU (tools/cu/tc_selftest.cu); what this pins is the layer in between -- argument
+order, physical layouts, permutes, autograd plumbing -- which otherwise only a GPU run would exercise.
+Nothing here is a product path: the product has no CPU fallback, the emulation exists only inside this test."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from u2pl_b200 import _lib, fused, ops
+
+
+def _addr(p):
+    return p.value if isinstance(p, ctypes.c_void_p) else (int(p) if p is not None else None)
+
+
+def _view(p, shape, dtype):
+    """Host memory at pointer p as a torch tensor (bf16 through its uint16 bit pattern)."""
+    a = _addr(p)
+    if a is None:
+        return None
+    n = int(np.prod(shape))
+    if dtype is torch.bfloat16:
+        arr = np.ctypeslib.as_array((ctypes.c_uint16 * n).from_address(a))
+        return torch.from_numpy(arr).view(torch.bfloat16).view(*shape)
+    arr = np.ctypeslib.as_array((ctypes.c_float * n).from_address(a))
+    return torch.from_numpy(arr).view(*shape)
+
+
+class FakeLib:
+    """Semantics of include/u2pl_b200.h for the entry points the glue under test calls."""
+
+    def u2pl_conv_bf16_nhwc(self, x, w, out, n, h, wd, cin, cout, k, d, scale, shift, res, relu, stream):
+        xt = _view(x, (n, h, wd, cin), torch.bfloat16).float().permute(0, 3, 1, 2)
+        wt = _view(w, (cout, k, k, cin), torch.bfloat16).float().permute(0, 3, 1, 2)
+        y = F.conv2d(xt, wt, None, 1, d * (k // 2), d)
+        if _addr(scale) is not None:
+            y = y * _view(scale, (cout,), torch.float32)[None, :, None, None]
+        if _addr(shift) is not None:
+            y = y + _view(shift, (cout,), torch.float32)[None, :, None, None]
+        if _addr(res) is not None:
+            y = y + _view(res, (n, h, wd, cout), torch.bfloat16).float().permute(0, 3, 1, 2)
+        if relu:
+            y = F.relu(y)
+        _view(out, (n, h, wd, cout), torch.bfloat16).copy_(y.permute(0, 2, 3, 1).bfloat16())
+        return 0
+
+    def u2pl_conv_stat_parts(self, n, h, w, k):
+        return (n * h * w + 127) // 128 if k == 1 else n * ((h + 7) // 8) * ((w + 15) // 16)
+
+    def u2pl_conv_bf16_nhwc_stats(self, x, w, out, n, h, wd, cin, cout, k, d, part, sums, stream):
+        self.u2pl_conv_bf16_nhwc(x, w, out, n, h, wd, cin, cout, k, d, None, None, None, 0, stream)
+        y = _view(out, (n * h * wd, cout), torch.bfloat16).float()
+        _view(sums, (2, cout), torch.float32).copy_(torch.stack([y.sum(0), (y * y).sum(0)]))
+        return 0
+
+    def u2pl_conv_wgrad_splits(self, n, h, w, cin, cout):
+        return 3
+
+    def u2pl_conv_wgrad_bf16_nhwc(self, x, g, part, n, h, wd, cin, cout, d, stream):
+        xt = _view(x, (n, h, wd, cin), torch.bfloat16).float().permute(0, 3, 1, 2)
+        gt = _view(g, (n, h, wd, cout), torch.bfloat16).float().permute(0, 3, 1, 2)
+        with torch.enable_grad():                                          # (this fake may run inside an autograd backward)
+            wz = torch.zeros(cout, cin, 3, 3, requires_grad=True)
+            F.conv2d(xt, wz, None, 1, d, d).backward(gt)
+        dw = wz.grad.permute(2, 3, 0, 1).reshape(9, cout, cin)           # [tap][co][ci]
+        p = _view(part, (3, 9, cout, cin), torch.float32)
+        p[0].copy_(dw * 0.5); p[1].copy_(dw * 0.25); p[2].copy_(dw * 0.25)   # the caller must sum the splits
+        return 0
+
+    def u2pl_bn_fold(self, C, gamma, beta, mean, var, eps, scale, shift, stream):
+        g, b = _view(gamma, (C,), torch.float32), _view(beta, (C,), torch.float32)
+        m, v = _view(mean, (C,), torch.float32), _view(var, (C,), torch.float32)
+        s = g / torch.sqrt(v + eps)
+        _view(scale, (C,), torch.float32).copy_(s)
+        _view(shift, (C,), torch.float32).copy_(b - m * s)
+        return 0
+
+    # ---- csrc/bn.cu entry points (x / y / dy / residual: [M, C] bf16 rows = channels-last pixels)
+    def u2pl_bn_parts(self):
+        return 4
+
+    def u2pl_bn_stats(self, x, M, C, partial, sums, stream):
+        xv = _view(x, (M, C), torch.bfloat16).float()
+        _view(sums, (2, C), torch.float32).copy_(torch.stack([xv.sum(0), (xv * xv).sum(0)]))
+        return 0
+
+    def u2pl_bn_finalize(self, sums, C, count, gamma, beta, rmean, rvar, momentum, eps, mean, invstd, scale, shift, stream):
+        n = count.value if hasattr(count, "value") else float(count)
+        sm = _view(sums, (2, C), torch.float32).double()
+        mu = sm[0] / n
+        var = (sm[1] / n - mu * mu).clamp_min(0)
+        inv = 1.0 / torch.sqrt(var + eps)
+        g, b = _view(gamma, (C,), torch.float32).double(), _view(beta, (C,), torch.float32).double()
+        _view(mean, (C,), torch.float32).copy_(mu.float())
+        _view(invstd, (C,), torch.float32).copy_(inv.float())
+        _view(scale, (C,), torch.float32).copy_((g * inv).float())
+        _view(shift, (C,), torch.float32).copy_((b - mu * g * inv).float())
+        rm, rv = _view(rmean, (C,), torch.float32), _view(rvar, (C,), torch.float32)
+        rm.mul_(1 - momentum).add_(momentum * mu.float())
+        rv.mul_(1 - momentum).add_(momentum * (var * n / (n - 1)).float())
+        return 0
+
+    def u2pl_bn_apply(self, x, res, scale, shift, M, C, relu, y, stream):
+        v = _view(x, (M, C), torch.bfloat16).float() * _view(scale, (C,), torch.float32) + _view(shift, (C,), torch.float32)
+        if _addr(res) is not None:
+            v = v + _view(res, (M, C), torch.bfloat16).float()
+        _view(y, (M, C), torch.bfloat16).copy_((F.relu(v) if relu else v).bfloat16())
+        return 0
+
+    @staticmethod
+    def _masked(dy, y, M, C):
+        g = _view(dy, (M, C), torch.bfloat16).float()
+        return g * (_view(y, (M, C), torch.bfloat16).float() > 0) if _addr(y) is not None else g
+
+    def u2pl_bn_backward_reduce(self, dy, x, y, mean, invstd, M, C, partial, sums, stream):
+        g = self._masked(dy, y, M, C)
+        xh = (_view(x, (M, C), torch.bfloat16).float() - _view(mean, (C,), torch.float32)) * _view(invstd, (C,), torch.float32)
+        _view(sums, (2, C), torch.float32).copy_(torch.stack([g.sum(0), (g * xh).sum(0)]))
+        return 0
+
+    def u2pl_bn_backward_elemt(self, dy, x, y, mean, invstd, gamma, sums, count, M, C, coef, dx, dres, stream):
+        n = count.value if hasattr(count, "value") else float(count)
+        g = self._masked(dy, y, M, C)
+        sm = _view(sums, (2, C), torch.float32)
+        inv, mu, ga = _view(invstd, (C,), torch.float32), _view(mean, (C,), torch.float32), _view(gamma, (C,), torch.float32)
+        A = ga * inv
+        B = -ga * inv * inv * sm[1] / n
+        D = -A * sm[0] / n - B * mu
+        _view(dx, (M, C), torch.bfloat16).copy_((A * g + B * _view(x, (M, C), torch.bfloat16).float() + D).bfloat16())
+        if _addr(dres) is not None:
+            _view(dres, (M, C), torch.bfloat16).copy_(g.bfloat16())
+        return 0
+
+    def u2pl_last_error(self):
+        return b""
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    fake = FakeLib()
+    monkeypatch.setattr(_lib, "load", lambda *a, **k: fake)
+    monkeypatch.setattr(ops, "_need_cuda", lambda *ts: None)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(fused, "_stream", lambda: None)
+    monkeypatch.setattr(fused, "_is_cl_bf16", lambda x: x.dtype == torch.bfloat16 and x.dim() == 4
+                        and x.is_contiguous(memory_format=torch.channels_last))
+    return fake
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("k,d", [(1, 1), (3, 1), (3, 4)])
+def test_ops_conv_layouts(emulated, k, d):
+    torch.manual_seed(k + d)
+    x = _cl(torch.randn(2, 16, 9, 7).bfloat16())
+    w_cl = _cl((torch.randn(24, 16, k, k) / 4).bfloat16())
+    w_plain = w_cl.contiguous()                                            # NCHW-contiguous weight must give the same result
+    scale, shift = torch.rand(24) + 0.5, torch.randn(24)
+    res = _cl(torch.randn(2, 24, 9, 7).bfloat16())
+    ref = F.relu(F.conv2d(x.float(), w_cl.float(), None, 1, d * (k // 2), d) * scale[None, :, None, None]
+                 + shift[None, :, None, None] + res.float())
+    for w in (w_cl, w_plain, w_plain.float()):
+        y = ops.conv_bf16_nhwc(x, w, d, scale, shift, res, True)
+        assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+        assert (y.float() - ref).abs().max() <= 2e-2 * ref.abs().max()
+    y2, sums = ops.conv_bf16_nhwc_stats(x, w_cl, d)
+    raw = F.conv2d(x.float(), w_cl.float(), None, 1, d * (k // 2), d)
+    assert (y2.float() - raw).abs().max() <= 2e-2 * raw.abs().max()
+    assert torch.allclose(sums[0], y2.float().sum(dim=(0, 2, 3)), atol=1e-3) and sums.shape == (2, 24)
+
+
+def test_ops_wgrad_layout(emulated):
+    torch.manual_seed(0)
+    x = _cl(torch.randn(2, 16, 9, 7).bfloat16())
+    g = _cl(torch.randn(2, 8, 9, 7).bfloat16())
+    dw = ops.conv_wgrad_bf16_nhwc(x, g, 2)
+    w = torch.zeros(8, 16, 3, 3, requires_grad=True)
+    F.conv2d(x.float(), w, None, 1, 2, 2).backward(g.float())
+    assert dw.shape == (8, 16, 3, 3) and torch.allclose(dw, w.grad, atol=1e-3)
+
+
+@pytest.mark.parametrize("k,d,wgrad", [(3, 2, False), (3, 2, True), (1, 1, False)])
+def test_conv_tc_fn_autograd_plumbing(emulated, monkeypatch, k, d, wgrad):
+    monkeypatch.setitem(fused.ENABLED, "tc_wgrad", wgrad)
+    torch.manual_seed(k)
+    x = _cl(torch.randn(2, 16, 9, 7).bfloat16()).requires_grad_(True)
+    wm = nn.Parameter(_cl(torch.randn(8, 16, k, k) / 4))                   # fp32 master weight, channels-last
+    y = fused._ConvTCFn.apply(x, wm.to(torch.bfloat16), d)
+    g = _cl(torch.randn_like(y))
+    y.backward(g)
+    xr = x.detach().float().requires_grad_(True)
+    wr = wm.detach().bfloat16().float().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, 1, d * (k // 2), d)
+    yr.backward(g.float())
+    assert (y.float() - yr).abs().max() <= 2e-2 * yr.abs().max()
+    assert (x.grad.float() - xr.grad).abs().max() <= 2e-2 * xr.grad.abs().max()
+    assert wm.grad.dtype == torch.float32 and (wm.grad - wr.grad).abs().max() <= 2e-2 * wr.grad.abs().max()
+    ys, sums = fused._ConvTCFn.apply(x, wm.to(torch.bfloat16), d, True)   # statistics variant: same output, extra sums
+    assert torch.equal(ys, y) and sums.shape == (2, 8) and not sums.requires_grad
+
+
+def test_conv_bn_act_eval_path(emulated, monkeypatch):
+    monkeypatch.setitem(fused.ENABLED, "tc_conv", True)
+    torch.manual_seed(3)
+    conv = nn.Conv2d(16, 24, 3, padding=2, dilation=2, bias=False).to(memory_format=torch.channels_last)
+    bn = nn.BatchNorm2d(24).eval()
+    with torch.no_grad():
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0); bn.weight.uniform_(0.5, 1.5); bn.bias.normal_()
+    x = _cl(torch.randn(2, 16, 9, 7).bfloat16())
+    r = _cl(torch.randn(2, 24, 9, 7).bfloat16())
+    with torch.no_grad():
+        assert fused._tc_conv_ok(x, conv, bn, r)
+        got = fused.conv_bn_act(x, conv, bn, nn.ReLU(), r)
+        ref = F.relu(bn(F.conv2d(x.float(), conv.weight.bfloat16().float(), None, 1, 2, 2)) + r.float())
+        seq = nn.Sequential(conv, bn, nn.ReLU(), nn.Conv2d(24, 24, 1, bias=False).to(memory_format=torch.channels_last),
+                            nn.BatchNorm2d(24).eval())
+        out = fused.run_sequential(seq, x)
+        ref2 = seq[4](F.conv2d(F.relu(bn(F.conv2d(x.float(), conv.weight.bfloat16().float(), None, 1, 2, 2))).bfloat16().float(),
+                               seq[3].weight.bfloat16().float()))
+    assert got.dtype == torch.bfloat16 and (got.float() - ref).abs().max() <= 3e-2 * ref.abs().max()
+    assert (out.float() - ref2).abs().max() <= 3e-2 * ref2.abs().max()
+    with torch.enable_grad():                                              # autograd on -> not the fused eval path
+        assert not fused._tc_conv_ok(x, conv, bn, None)
+
+
+@pytest.mark.parametrize("train,relu,res", [(True, True, True), (True, False, False), (False, True, True), (True, True, False)])
+def test_bn_act_function_matches_batchnorm(emulated, train, relu, res):
+    """fused._BNAct (the DEFAULT path's Python) over the emulated csrc/bn.cu ABI against nn.BatchNorm2d autograd."""
+    torch.manual_seed(int(train) * 4 + int(relu) * 2 + int(res))
+    C = 16
+    x32 = torch.randn(3, C, 7, 5).bfloat16().float()
+    r32 = torch.randn(3, C, 7, 5).bfloat16().float() if res else None
+    bn, ref = nn.BatchNorm2d(C), nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.5, 0.5); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2)
+    ref.load_state_dict(bn.state_dict())
+    bn.train(train); ref.train(train)
+    xa = _cl(x32.bfloat16()).requires_grad_(True)
+    ra = _cl(r32.bfloat16()).requires_grad_(True) if res else None
+    y = fused.bn_act(xa, bn, nn.ReLU() if relu else None, ra)
+    xb = x32.clone().requires_grad_(True)
+    rb = r32.clone().requires_grad_(True) if res else None
+    yr = ref(xb)
+    yr = yr + rb if res else yr
+    yr = F.relu(yr) if relu else yr
+    assert y.dtype == torch.bfloat16 and (y.float() - yr).abs().max() <= 3e-2 * max(1.0, yr.abs().max().item())
+    assert torch.allclose(bn.running_mean, ref.running_mean, atol=1e-4) and torch.allclose(bn.running_var, ref.running_var, atol=1e-3)
+    if train:
+        g = torch.randn_like(yr).bfloat16().float()
+        y.backward(_cl(g.bfloat16()))
+        yr.backward(g)
+        assert (xa.grad.float() - xb.grad).abs().max() <= 4e-2 * max(1.0, xb.grad.abs().max().item())
+        assert torch.allclose(bn.weight.grad, ref.weight.grad, atol=3e-2 * ref.weight.grad.abs().max().item())
+        assert torch.allclose(bn.bias.grad, ref.bias.grad, atol=3e-2 * ref.bias.grad.abs().max().item())
+        if res:
+            assert (ra.grad.float() - rb.grad).abs().max() <= 2e-2 * max(1.0, rb.grad.abs().max().item())
+        assert int(bn.num_batches_tracked) == 1
+
+
+def test_train_mode_conv_stats_bn_chain(emulated, monkeypatch):
+    """U2PL_TC_TRAIN routing: conv (+statistics epilogue) -> _BNAct consuming those sums, against Conv2d + BatchNorm2d."""
+    monkeypatch.setitem(fused.ENABLED, "tc_train", True)
+    torch.manual_seed(5)
+    conv = nn.Conv2d(16, 24, 3, padding=2, dilation=2, bias=False).to(memory_format=torch.channels_last)
+    bn = nn.BatchNorm2d(24)
+    conv_r, bn_r = nn.Conv2d(16, 24, 3, padding=2, dilation=2, bias=False), nn.BatchNorm2d(24)
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.bfloat16().float())
+    conv_r.load_state_dict(conv.state_dict()); bn_r.load_state_dict(bn.state_dict())
+    x32 = torch.randn(2, 16, 9, 7).bfloat16().float()
+    xa = _cl(x32.bfloat16()).requires_grad_(True)
+    calls = []
+    real = emulated.u2pl_bn_stats
+    monkeypatch.setattr(emulated, "u2pl_bn_stats", lambda *a: (calls.append(1), real(*a))[1])
+    y = fused.conv_bn_act(xa, conv, bn, nn.ReLU())
+    assert not calls                                                       # statistics came from the conv epilogue
+    xb = x32.clone().requires_grad_(True)
+    yr = F.relu(bn_r(conv_r(xb)))
+    assert (y.float() - yr).abs().max() <= 4e-2 * max(1.0, yr.abs().max().item())
+    g = torch.randn_like(yr).bfloat16().float()
+    y.backward(_cl(g.bfloat16()))
+    yr.backward(g)
+    assert (xa.grad.float() - xb.grad).abs().max() <= 6e-2 * max(1.0, xb.grad.abs().max().item())
+    assert (conv.weight.grad - conv_r.weight.grad).abs().max() <= 6e-2 * conv_r.weight.grad.abs().max().item()
+    assert torch.allclose(bn.running_var, bn_r.running_var, atol=2e-3)
