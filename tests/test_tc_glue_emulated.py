@@ -293,3 +293,62 @@ def test_train_mode_conv_stats_bn_chain(emulated, monkeypatch):
     assert (xa.grad.float() - xb.grad).abs().max() <= 6e-2 * max(1.0, xb.grad.abs().max().item())
     assert (conv.weight.grad - conv_r.weight.grad).abs().max() <= 6e-2 * conv_r.weight.grad.abs().max().item()
     assert torch.allclose(bn.running_var, bn_r.running_var, atol=2e-3)
+
+
+def _small_net():
+    import copy
+    import u2pl_b200
+    u2pl_b200.install()
+    from u2pl.models.model_helper import ModelBuilder
+    net = {"num_classes": 21, "sync_bn": False, "ema_decay": 0.99,
+           "encoder": {"type": "u2pl.models.resnet.resnet50",
+                       "kwargs": {"multi_grid": True, "zero_init_residual": False, "fpn": True,
+                                  "replace_stride_with_dilation": [False, True, True], "pretrained": False}},
+           "decoder": {"type": "u2pl.models.decoder.dec_deeplabv3_plus", "kwargs": {"inner_planes": 256, "dilations": [12, 24, 36]}}}
+    torch.manual_seed(0)
+    m = ModelBuilder(copy.deepcopy(net)).to(memory_format=torch.channels_last)
+    for mod in m.modules():
+        if isinstance(mod, nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+    return m
+
+
+def test_whole_network_eval_routing(emulated, monkeypatch):
+    """Mirror network, eval / no_grad / bf16 autocast: every eligible conv+BN(+residual)(+ReLU) group through the fused
+    tensor-core entry point (U2PL_TC_CONV) vs the default routing (conv module + BN kernel) -- same network output."""
+    m = _small_net().eval()
+    x = _cl(torch.randn(1, 3, 49, 49))
+    outs, convs = {}, []
+    real = emulated.u2pl_conv_bf16_nhwc
+    monkeypatch.setattr(emulated, "u2pl_conv_bf16_nhwc", lambda *a: (convs.append(a[8:10]), real(*a))[1])
+    for flag in (False, True):
+        monkeypatch.setitem(fused.ENABLED, "tc_conv", flag)
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            outs[flag] = {k: v.float() for k, v in m(x).items()}
+    assert len(convs) >= 50                                               # 16 bottlenecks x 3 + downsamples + ASPP + decoder
+    assert {int(d[1]) for d in convs} >= {1, 2, 4, 8, 16, 12, 24, 36}      # every dilation of the network went through it
+    for k in ("pred", "rep"):
+        a, b = outs[False][k], outs[True][k]
+        assert (a - b).norm() <= 0.05 * a.norm(), (k, float((a - b).norm() / a.norm()))
+
+
+def test_whole_encoder_train_routing(emulated, monkeypatch):
+    """Train mode with autograd: U2PL_TC_TRAIN (+ tensor-core weight gradients) routing vs the default routing."""
+    import copy
+    ma = _small_net().train()
+    mb = copy.deepcopy(ma)
+    x = _cl(torch.randn(2, 3, 33, 33))
+    res = []
+    for m, flag in ((ma, False), (mb, True)):
+        monkeypatch.setitem(fused.ENABLED, "tc_train", flag)
+        monkeypatch.setitem(fused.ENABLED, "tc_wgrad", flag)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            feats = m.encoder(x)
+        sum(t.float().pow(2).mean() for t in feats).backward()
+        res.append((feats, dict(m.named_parameters())))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert (a.float() - b.float()).norm() <= 0.05 * a.float().norm()
+    for name in ("encoder.layer4.2.conv2.weight", "encoder.layer3.1.conv1.weight", "encoder.layer1.0.bn1.weight", "encoder.conv1.3.weight"):
+        ga, gb = res[0][1][name].grad.float(), res[1][1][name].grad.float()
+        assert (ga - gb).norm() <= 0.15 * ga.norm(), (name, float((ga - gb).norm() / ga.norm()))
