@@ -248,8 +248,15 @@ int main(int argc, char **argv)
         fails += check_conv(L, 1, 72, 20, 24, 40, 3, 3, true, false);        // Cin % 64 != 0, epilogue, 128-wide tile
         fails += check_conv(L, 2, 128, 17, 33, 256, 3, 2, true, false);      // two K blocks per tap, 256-wide tile
     }
-    if (all || !strcmp(what, "stats")) fails += check_conv(L, 2, 64, 17, 19, 128, 3, 1, false, true);
-    if (all || !strcmp(what, "wgrad")) fails += check_wgrad(L, 1, 264, 7, 17, 136, 2);
+    if (all || !strcmp(what, "stats")) {
+        fails += check_conv(L, 2, 64, 17, 19, 128, 3, 1, false, true);
+        fails += check_conv(L, 1, 128, 20, 35, 256, 3, 2, false, true);      // 256-wide tile (largest shared-memory footprint)
+        fails += check_conv(L, 3, 64, 5, 7, 264, 1, 1, false, true);         // flat 1x1, partial channel tile
+    }
+    if (all || !strcmp(what, "wgrad")) {
+        fails += check_wgrad(L, 1, 264, 7, 17, 136, 2);
+        fails += check_wgrad(L, 2, 512, 9, 20, 256, 12);                     // taps that fall entirely outside the map, 2 ci tiles
+    }
     if (!strcmp(what, "perf")) { perf(L); return 0; }
     printf("%s\n", fails ? "SELFTEST FAILED" : "SELFTEST PASSED");
     return fails ? 1 : 0;
