@@ -299,6 +299,17 @@ int u2pl_conv_bf16_nhwc_stats(const void *x, const void *wgt, void *out, int64_t
                               int64_t cin, int64_t cout, int ksize, int dilation, float *stat_part, float *sums,
                               void *stream);
 
+/* General form: additionally applies act_in(x * in_scale[ci] + in_shift[ci]) to the INPUT while its tiles sit in shared
+ * memory (in_scale / in_shift [cin] or NULL, in_relu) -- i.e. the previous layer's train-mode BatchNorm + ReLU is folded
+ * into this convolution's operand load, so the normalised activation never exists in HBM; zero padding applies to the
+ * activated tensor.  Any combination with the output epilogue (scale/shift/residual/relu) and the statistics epilogue
+ * (stat_part + sums, both or neither) is allowed.
+ * replaces: bn(x) -> relu -> conv chains inside Bottleneck.forward (resnet.py:118-131) on the train-mode forwards. */
+int u2pl_conv_bf16_nhwc_ex(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w, int64_t cin,
+                           int64_t cout, int ksize, int dilation, const float *in_scale, const float *in_shift,
+                           int in_relu, const float *scale, const float *shift, const void *residual, int relu,
+                           float *stat_part, float *sums, void *stream);
+
 /* Weight gradient of the same stride-1 "same" 3x3 (dilated) convolution on the tensor cores, operands read in place
  * from the channels-last tensors (both are MN-major for this contraction; no transposes, no cropped copies):
  *   partial[s][r*3+s'][co][ci] = sum over the pixels of K-split s of gout[n,h,w,co] * x[n,h+(r-1)d,w+(s'-1)d,ci]

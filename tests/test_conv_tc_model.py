@@ -36,7 +36,7 @@ def _wbox(wmat, k0, n0, BN):
     return out
 
 
-def conv_model(x_nhwc, w_ocrs_c, ksize, dil, flat):
+def conv_model(x_nhwc, w_ocrs_c, ksize, dil, flat, in_affine=None):
     N, H, W, Cin = x_nhwc.shape
     Cout = w_ocrs_c.shape[0]
     wmat = w_ocrs_c.reshape(Cout, -1)                         # [Cout, R*S*Cin]: memory order of a channels-last weight
@@ -56,12 +56,23 @@ def conv_model(x_nhwc, w_ocrs_c, ksize, dil, flat):
         h0, w0 = (rem // tiles_w) * th, (rem % tiles_w) * tw
         for n0 in range(0, Cout, BN):
             acc = np.zeros((BM, BN), np.float32)
-            for tap in range(ksize * ksize):
+            order = [(tap, kb) for tap in range(ksize * ksize) for kb in range(kb_per_tap)]
+            if in_affine is not None:                         # kXform: channel block outer, tap inner
+                order = [(tap, kb) for kb in range(kb_per_tap) for tap in range(ksize * ksize)]
+            for tap, kb in order:
                 dh, dw = (tap // ksize - ksize // 2) * dil, (tap % ksize - ksize // 2) * dil
-                for kb in range(kb_per_tap):
-                    a = _box(xv, kb * BK, w0 + dw, h0 + dh, img, tw, th)
-                    b = _wbox(wmat, tap * Cin + kb * BK, n0, BN)
-                    acc += a @ b.T
+                a = _box(xv, kb * BK, w0 + dw, h0 + dh, img, tw, th)
+                if in_affine is not None:                     # transform warps: per row (pixel) mask, per chunk channels
+                    sc, sh = in_affine
+                    for r in range(BM):
+                        hh, ww = h0 + dh + (r >> log2_tw), w0 + dw + (r & (tw - 1))
+                        if 0 <= hh < Hh and 0 <= ww < Ww:
+                            for c in range(BK):
+                                ch = kb * BK + c
+                                s_, b_ = (sc[ch], sh[ch]) if ch < Cin else (0.0, 0.0)
+                                a[r, c] = max(a[r, c] * s_ + b_, 0.0)
+                b = _wbox(wmat, tap * Cin + kb * BK, n0, BN)
+                acc += a @ b.T
             for m in range(BM):                               # epilogue: one thread per accumulator row
                 h, w = h0 + (m >> log2_tw), w0 + (m & (tw - 1))
                 if h < Hh and w < Ww:
@@ -81,6 +92,19 @@ def test_conv_addressing_model(N, Cin, H, W, Cout, k, d):
     w = torch.randn(Cout, Cin, k, k, generator=g)
     ref = F.conv2d(x, w, None, 1, d * (k // 2), d).permute(0, 2, 3, 1).numpy()
     got = conv_model(x.permute(0, 2, 3, 1).contiguous().numpy(), w.permute(0, 2, 3, 1).contiguous().numpy(), k, d, flat=(k == 1))
+    assert np.abs(got - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,d", [(2, 72, 11, 19, 40, 3, 2), (2, 24, 5, 7, 16, 1, 1)])
+def test_conv_in_transform_model(N, Cin, H, W, Cout, k, d):
+    """kXform: relu(x * s + t) applied to the A tiles in shared memory; padding pixels and channels beyond Cin stay zero."""
+    g = torch.Generator().manual_seed(Cin + k)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g)
+    sc, sh = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g)
+    ref = F.conv2d(F.relu(x * sc[None, :, None, None] + sh[None, :, None, None]), w, None, 1, d * (k // 2), d).permute(0, 2, 3, 1).numpy()
+    got = conv_model(x.permute(0, 2, 3, 1).contiguous().numpy(), w.permute(0, 2, 3, 1).contiguous().numpy(), k, d, flat=(k == 1),
+                     in_affine=(sc.numpy(), sh.numpy()))
     assert np.abs(got - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
 
 

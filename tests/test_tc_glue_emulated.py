@@ -52,6 +52,20 @@ class FakeLib:
         _view(out, (n, h, wd, cout), torch.bfloat16).copy_(y.permute(0, 2, 3, 1).bfloat16())
         return 0
 
+    def u2pl_conv_bf16_nhwc_ex(self, x, w, out, n, h, wd, cin, cout, k, d, in_scale, in_shift, in_relu, scale, shift, res, relu,
+                               part, sums, stream):
+        xt = _view(x, (n, h, wd, cin), torch.bfloat16).float()
+        if _addr(in_scale) is not None:
+            xt = xt * _view(in_scale, (cin,), torch.float32)
+        if _addr(in_shift) is not None:
+            xt = xt + _view(in_shift, (cin,), torch.float32)
+        z = (F.relu(xt) if in_relu else xt).bfloat16().contiguous()      # the kernel rewrites the tile in bf16
+        rc = self.u2pl_conv_bf16_nhwc(ctypes.c_void_p(z.data_ptr()), w, out, n, h, wd, cin, cout, k, d, scale, shift, res, relu, stream)
+        if _addr(sums) is not None:
+            y = _view(out, (n * h * wd, cout), torch.bfloat16).float()
+            _view(sums, (2, cout), torch.float32).copy_(torch.stack([y.sum(0), (y * y).sum(0)]))
+        return rc
+
     def u2pl_conv_stat_parts(self, n, h, w, k):
         return (n * h * w + 127) // 128 if k == 1 else n * ((h + 7) // 8) * ((w + 15) // 16)
 
@@ -177,6 +191,22 @@ def test_ops_conv_layouts(emulated, k, d):
     raw = F.conv2d(x.float(), w_cl.float(), None, 1, d * (k // 2), d)
     assert (y2.float() - raw).abs().max() <= 2e-2 * raw.abs().max()
     assert torch.allclose(sums[0], y2.float().sum(dim=(0, 2, 3)), atol=1e-3) and sums.shape == (2, 24)
+
+
+def test_ops_conv_ex_argument_order(emulated):
+    torch.manual_seed(9)
+    x = _cl(torch.randn(2, 16, 9, 7).bfloat16())
+    w = _cl((torch.randn(24, 16, 3, 3) / 4).bfloat16())
+    isc, ish = torch.rand(16) + 0.5, torch.randn(16)
+    sc, sh = torch.rand(24) + 0.5, torch.randn(24)
+    res = _cl(torch.randn(2, 24, 9, 7).bfloat16())
+    z = F.relu(x.float() * isc[None, :, None, None] + ish[None, :, None, None]).bfloat16().float()
+    ref = F.relu(F.conv2d(z, w.float(), None, 1, 2, 2) * sc[None, :, None, None] + sh[None, :, None, None] + res.float())
+    y, sums = ops.conv_bf16_nhwc_ex(x, w, 2, isc, ish, True, sc, sh, res, True, want_stats=True)
+    assert (y.float() - ref).abs().max() <= 2e-2 * ref.abs().max()
+    assert torch.allclose(sums[1], (y.float() ** 2).sum(dim=(0, 2, 3)), rtol=1e-4)
+    y2 = ops.conv_bf16_nhwc_ex(x, w, 2)                                     # everything optional off == plain convolution
+    assert (y2.float() - F.conv2d(x.float(), w.float(), None, 1, 2, 2)).abs().max() <= 2e-2 * 8
 
 
 def test_ops_wgrad_layout(emulated):

@@ -2,7 +2,7 @@
 // u2pl_conv_bf16_nhwc (plain / epilogue / statistics) and u2pl_conv_wgrad_bf16_nhwc against CPU loops.
 // Starts in about a second (no Python, no torch import), so it fits in the smallest GPU slot:
 //   nvcc -O2 -std=c++17 -o tools/cu/tc_selftest.bin tools/cu/tc_selftest.cu -ldl     (built here, runs on the box)
-//   ./tools/cu/tc_selftest.bin [conv|stats|wgrad|all|perf]      (perf: CUDA-event timings at the network's layer shapes)
+//   ./tools/cu/tc_selftest.bin [conv|stats|xform|wgrad|all|perf]      (perf: CUDA-event timings at the network's layer shapes)
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -15,6 +15,8 @@
 typedef int (*conv_fn)(const void *, const void *, void *, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float *,
                        const float *, const void *, int, void *);
 typedef int (*conv_stats_fn)(const void *, const void *, void *, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, float *, float *, void *);
+typedef int (*conv_ex_fn)(const void *, const void *, void *, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, const float *,
+                          const float *, int, const float *, const float *, const void *, int, float *, float *, void *);
 typedef int64_t (*parts_fn)(int64_t, int64_t, int64_t, int);
 typedef int (*splits_fn)(int64_t, int64_t, int64_t, int64_t, int64_t);
 typedef int (*wgrad_fn)(const void *, const void *, float *, int64_t, int64_t, int64_t, int64_t, int64_t, int, void *);
@@ -45,7 +47,7 @@ template <typename T> static T *to_dev(const std::vector<T> &h)
     return d;
 }
 
-struct Lib { conv_fn conv; conv_stats_fn conv_stats; parts_fn parts; splits_fn splits; wgrad_fn wgrad; err_fn err; };
+struct Lib { conv_fn conv; conv_ex_fn conv_ex; conv_stats_fn conv_stats; parts_fn parts; splits_fn splits; wgrad_fn wgrad; err_fn err; };
 
 static int check_conv(const Lib &L, int N, int Cin, int H, int W, int Cout, int k, int d, bool epi, bool stats)
 {
@@ -120,6 +122,70 @@ static int check_conv(const Lib &L, int N, int Cin, int H, int W, int Cout, int 
     }
     printf("conv N=%d Cin=%d %dx%d Cout=%d k=%d d=%d epi=%d stats=%d: mismatches=%zu/%zu max_err=%g (ref max %g) stats_rel_err=%g  %s\n", N, Cin,
            H, W, Cout, k, d, epi, stats, bad, ny, worst, scale_ref, s_err, bad == 0 ? "OK" : "WRONG");
+    return bad == 0 ? 0 : 1;
+}
+
+// in-transform variant: relu(x * s + t) applied to the input in shared memory, plain output, optional statistics
+static int check_conv_xform(const Lib &L, int N, int Cin, int H, int W, int Cout, int k, int d, bool stats)
+{
+    const size_t nx = static_cast<size_t>(N) * H * W * Cin, nw = static_cast<size_t>(Cout) * k * k * Cin, ny = static_cast<size_t>(N) * H * W * Cout;
+    std::vector<uint16_t> x(nx), w(nw);
+    std::vector<float> is(Cin), it(Cin);
+    for (auto &v : x) v = f2bf(rnd());
+    for (auto &v : w) v = f2bf(rnd() / sqrtf(static_cast<float>(Cin * k * k)) * 3.0f);
+    for (int c = 0; c < Cin; ++c) { is[c] = 1.0f + 0.5f * rnd(); it[c] = 0.5f * rnd(); }
+    std::vector<float> z(nx), ref(ny);
+    for (size_t i = 0; i < nx; ++i) {                              // activated input, rounded to bf16 like the kernel's rewrite
+        float v = bf2f(x[i]) * is[i % Cin] + it[i % Cin];
+        z[i] = bf2f(f2bf(v > 0.0f ? v : 0.0f));
+    }
+    const int pad = d * (k / 2);
+    for (int n = 0; n < N; ++n)
+        for (int h = 0; h < H; ++h)
+            for (int ww = 0; ww < W; ++ww)
+                for (int co = 0; co < Cout; ++co) {
+                    float acc = 0.0f;
+                    for (int r = 0; r < k; ++r)
+                        for (int s = 0; s < k; ++s) {
+                            const int hi = h + r * d - pad, wi = ww + s * d - pad;
+                            if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+                            const float *zp = &z[((static_cast<size_t>(n) * H + hi) * W + wi) * Cin];
+                            const uint16_t *wp = &w[((static_cast<size_t>(co) * k + r) * k + s) * Cin];
+                            for (int ci = 0; ci < Cin; ++ci) acc += zp[ci] * bf2f(wp[ci]);
+                        }
+                    ref[((static_cast<size_t>(n) * H + h) * W + ww) * Cout + co] = acc;
+                }
+    uint16_t *dx = to_dev(x), *dw = to_dev(w), *dy = nullptr;
+    float *dis = to_dev(is), *dit = to_dev(it), *dpart = nullptr, *dsums = nullptr;
+    cudaMalloc(&dy, ny * 2);
+    cudaMemset(dy, 0xff, ny * 2);
+    if (stats) { cudaMalloc(&dpart, L.parts(N, H, W, k) * 2 * Cout * 4); cudaMalloc(&dsums, 2 * Cout * 4); }
+    const int rc = L.conv_ex(dx, dw, dy, N, H, W, Cin, Cout, k, d, dis, dit, 1, nullptr, nullptr, nullptr, 0, dpart, dsums, nullptr);
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (rc != 0 || e != cudaSuccess) { printf("conv_xform: rc=%d cuda=%s err=%s\n", rc, cudaGetErrorString(e), L.err()); return 1; }
+    std::vector<uint16_t> y(ny);
+    cudaMemcpy(y.data(), dy, ny * 2, cudaMemcpyDeviceToHost);
+    float worst = 0.0f, mx = 1.0f;
+    for (size_t i = 0; i < ny; ++i) mx = fmaxf(mx, fabsf(ref[i]));
+    size_t bad = 0;
+    for (size_t i = 0; i < ny; ++i) {
+        const float dlt = fabsf(bf2f(y[i]) - ref[i]);
+        if (!(dlt <= 1e-2f * mx)) ++bad;
+        if (dlt > worst || dlt != dlt) worst = dlt;
+    }
+    double s_err = 0.0;
+    if (stats) {
+        std::vector<float> sums(2 * Cout);
+        cudaMemcpy(sums.data(), dsums, 2 * Cout * 4, cudaMemcpyDeviceToHost);
+        for (int c = 0; c < Cout; ++c) {
+            double a = 0.0, b = 0.0;
+            for (size_t p = 0; p < static_cast<size_t>(N) * H * W; ++p) { const double v = bf2f(y[p * Cout + c]); a += v; b += v * v; }
+            s_err = fmax(s_err, fmax(fabs(a - sums[c]) / (1.0 + fabs(a)), fabs(b - sums[Cout + c]) / (1.0 + fabs(b))));
+        }
+        if (s_err > 1e-3) ++bad;
+    }
+    printf("conv_xform N=%d Cin=%d %dx%d Cout=%d k=%d d=%d stats=%d: mismatches=%zu/%zu max_err=%g (ref max %g) stats_rel_err=%g  %s\n", N, Cin, H, W,
+           Cout, k, d, stats, bad, ny, worst, mx, s_err, bad == 0 ? "OK" : "WRONG");
     return bad == 0 ? 0 : 1;
 }
 
@@ -235,12 +301,13 @@ int main(int argc, char **argv)
     if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
     Lib L;
     L.conv = reinterpret_cast<conv_fn>(dlsym(h, "u2pl_conv_bf16_nhwc"));
+    L.conv_ex = reinterpret_cast<conv_ex_fn>(dlsym(h, "u2pl_conv_bf16_nhwc_ex"));
     L.conv_stats = reinterpret_cast<conv_stats_fn>(dlsym(h, "u2pl_conv_bf16_nhwc_stats"));
     L.parts = reinterpret_cast<parts_fn>(dlsym(h, "u2pl_conv_stat_parts"));
     L.splits = reinterpret_cast<splits_fn>(dlsym(h, "u2pl_conv_wgrad_splits"));
     L.wgrad = reinterpret_cast<wgrad_fn>(dlsym(h, "u2pl_conv_wgrad_bf16_nhwc"));
     L.err = reinterpret_cast<err_fn>(dlsym(h, "u2pl_last_error"));
-    if (!L.conv || !L.conv_stats || !L.parts || !L.splits || !L.wgrad || !L.err) { fprintf(stderr, "missing symbol\n"); return 2; }
+    if (!L.conv || !L.conv_ex || !L.conv_stats || !L.parts || !L.splits || !L.wgrad || !L.err) { fprintf(stderr, "missing symbol\n"); return 2; }
     int fails = 0;
     const bool all = !strcmp(what, "all");
     if (all || !strcmp(what, "conv")) {
@@ -252,6 +319,11 @@ int main(int argc, char **argv)
         fails += check_conv(L, 2, 64, 17, 19, 128, 3, 1, false, true);
         fails += check_conv(L, 1, 128, 20, 35, 256, 3, 2, false, true);      // 256-wide tile (largest shared-memory footprint)
         fails += check_conv(L, 3, 64, 5, 7, 264, 1, 1, false, true);         // flat 1x1, partial channel tile
+    }
+    if (all || !strcmp(what, "xform")) {
+        fails += check_conv_xform(L, 2, 72, 11, 19, 40, 3, 2, false);        // Cin % 64 != 0, padding rows, 128-wide tile
+        fails += check_conv_xform(L, 1, 128, 20, 35, 256, 3, 1, true);       // two channel blocks x nine taps, statistics
+        fails += check_conv_xform(L, 3, 64, 5, 7, 136, 1, 1, false);         // flat 1x1, rows beyond the tensor
     }
     if (all || !strcmp(what, "wgrad")) {
         fails += check_wgrad(L, 1, 264, 7, 17, 136, 2);

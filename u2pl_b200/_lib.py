@@ -52,6 +52,8 @@ SIGNATURES = {
     "u2pl_conv_bf16_nhwc": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, _P, _P, _P, c_int, _S]),
     "u2pl_conv_stat_parts": (c_int64, [c_int64, c_int64, c_int64, c_int]),
     "u2pl_conv_bf16_nhwc_stats": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, _P, _P, _S]),
+    "u2pl_conv_bf16_nhwc_ex": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, _P, _P, c_int,
+                                       _P, _P, _P, c_int, _P, _P, _S]),
     "u2pl_conv_wgrad_splits": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int64]),
     "u2pl_conv_wgrad_bf16_nhwc": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, _S]),
     "u2pl_bn_parts": (c_int64, []),

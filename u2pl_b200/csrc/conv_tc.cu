@@ -49,10 +49,18 @@ struct ConvParams {
     int relu;
     __nv_bfloat16 *D;
     float *stat_part;                 // kStats only: [pixel tiles][2][Cout] per-tile sum / sum of squares of the STORED values
+    const float *in_scale, *in_shift; // kXform only: [Cin] affine applied to x while it sits in shared memory
+    int in_relu;                      //              followed by max(., 0)
 };
 
-template <int kBN, bool kStats>
-__global__ void __launch_bounds__(convtc::kThreads, 1)
+// kXform: the input tensor is the RAW output of the previous convolution and its BatchNorm (+ReLU) is applied here,
+// on the A tile, between the TMA load and the MMA: four extra warps rewrite each stage in place (16-byte chunks, the
+// SWIZZLE_128B pattern followed by hand), make the writes visible to the async proxy and hand the stage to the MMA warp
+// through `ready`.  Pixels outside the image stay zero (the padding applies to the activated tensor).  The K loop runs
+// channel-block-outer / tap-inner in this variant so that a thread's 8 channels -- its 16 scale/shift values -- stay in
+// registers for nine consecutive stages.
+template <int kBN, bool kStats, bool kXform>
+__global__ void __launch_bounds__(kXform ? convtc::kThreads + 128 : convtc::kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, ConvParams p)
 {
     using namespace convtc;
@@ -67,7 +75,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
     float *s_par = reinterpret_cast<float *>(tmem_slot + 2);      // [2 stages][scale kBN | shift kBN]
     float *s_tr = s_par + 4 * kBN;                                // kStats: [4 warps][32 rows][33] transpose buffers
-    float *s_red = s_tr + 4 * 32 * 33;                            // kStats: [4 warps][kBN][2] per-warp column sums
+    float *s_red = s_tr + (kStats ? 4 * 32 * 33 : 0);             // kStats: [4 warps][kBN][2] per-warp column sums
+    uint64_t *ready = reinterpret_cast<uint64_t *>(s_red + (kStats ? 4 * kBN * 2 : 0));   // kXform: [kStages] transform -> MMA
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tw = 1 << p.log2_tw, th = kBM >> p.log2_tw;
@@ -82,6 +91,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4); }
+        if (kXform)
+            for (int s = 0; s < kStages; ++s) mbar_init(ready + s, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -100,9 +111,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const int tm = t / tiles_n, n0 = (t % tiles_n) * kBN;
                 const int img = tm / tiles_img, rem = tm % tiles_img;
                 const int h0 = (rem / p.tiles_w) * th, w0 = (rem % p.tiles_w) * tw;
-                for (int tap = 0; tap < p.R * p.S; ++tap) {
-                    const int dh = (tap / p.S - p.R / 2) * p.dil, dw = (tap % p.S - p.S / 2) * p.dil;
-                    for (int kb = 0; kb < kb_per_tap; ++kb, ++it) {
+                const int taps = p.R * p.S;
+                for (int step = 0; step < nkb; ++step, ++it) {
+                    {   // kXform: channel block outer, tap inner; otherwise tap outer, channel block inner
+                        const int tap = kXform ? step % taps : step / kb_per_tap;
+                        const int kb = kXform ? step / taps : step % kb_per_tap;
+                        const int dh = (tap / p.S - p.R / 2) * p.dil, dw = (tap % p.S - p.S / 2) * p.dil;
                         const int s = it % kStages;
                         mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
                         mbar_expect_tx(full + s, kTileABytes + kTileBBytes);
@@ -126,7 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const uint32_t d_tmem = tmem_base + acc * kTmemCols;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % kStages;
-                    mbar_wait(full + s, (it / kStages) & 1);
+                    mbar_wait(kXform ? ready + s : full + s, (it / kStages) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a0 = smem_u32(sA + s * kTileABytes), b0 = smem_u32(sB + s * kTileBBytes);
 #pragma unroll
@@ -137,7 +151,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 umma_commit(tmem_full + acc);
             }
         }
-    } else {                                          // ---------------- epilogue (warps 2..5)
+    } else if (kXform && warp >= 6) {                 // ---------------- A-tile transform (warps 6..9)
+        const int tid = threadIdx.x - kThreads;       // 0..127: chunk = 8 channels, rows rbase + 16 i
+        const int chunk = tid & 7, rbase = tid >> 3;
+        const int taps = p.R * p.S;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int tm = t / tiles_n;
+            const int img = tm / tiles_img, rem = tm % tiles_img;
+            const int h0 = (rem / p.tiles_w) * th, w0 = (rem % p.tiles_w) * tw;
+            (void)img;
+            for (int kb = 0; kb < kb_per_tap; ++kb) {
+                float sc[8], sh[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {         // channels beyond Cin (zero-filled by TMA) must stay zero
+                    const int c = kb * kBK + chunk * 8 + e;
+                    sc[e] = (c < p.Cin && p.in_scale) ? __ldg(p.in_scale + c) : (c < p.Cin ? 1.0f : 0.0f);
+                    sh[e] = (c < p.Cin && p.in_shift) ? __ldg(p.in_shift + c) : 0.0f;
+                }
+                for (int tap = 0; tap < taps; ++tap, ++it) {
+                    const int dh = (tap / p.S - p.R / 2) * p.dil, dw = (tap % p.S - p.S / 2) * p.dil;
+                    const int s = it % kStages;
+                    mbar_wait(full + s, (it / kStages) & 1);
+                    uint8_t *tile = sA + s * kTileABytes;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = rbase + 16 * i;
+                        const int hh = h0 + dh + (r >> p.log2_tw), ww = w0 + dw + (r & (tw - 1));
+                        if (static_cast<unsigned>(hh) < static_cast<unsigned>(p.H) && static_cast<unsigned>(ww) < static_cast<unsigned>(p.W)) {
+                            uint4 *cp = reinterpret_cast<uint4 *>(tile + r * 128 + ((chunk ^ (r & 7)) << 4));
+                            uint4 v = *cp;
+                            __nv_bfloat162 *hv = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 f = __bfloat1622float2(hv[e]);
+                                f.x = fmaf(f.x, sc[2 * e], sh[2 * e]);
+                                f.y = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+                                if (p.in_relu) { f.x = fmaxf(f.x, 0.0f); f.y = fmaxf(f.y, 0.0f); }
+                                hv[e] = __floats2bfloat162_rn(f.x, f.y);
+                            }
+                            *cp = v;
+                        }                             // rows outside the image were zero-filled and stay zero (padding)
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(ready + s);
+                }
+            }
+        }
+    } else if (warp >= 2 && warp < 6) {               // ---------------- epilogue (warps 2..5)
         const int q = warp & 3;
         const bool affine = p.scale != nullptr || p.shift != nullptr;
         const int m = q * 32 + lane, ti = m >> p.log2_tw, tj = m & (tw - 1);
@@ -285,8 +347,21 @@ static bool make_map_weight(CUtensorMap *map, const void *base, int64_t cout, in
 
 using namespace u2pl;
 
+template <int kBN, bool kStats, bool kXform>
+static cudaError_t conv_configure(size_t smem)
+{
+    return cudaFuncSetAttribute(conv_tc_kernel<kBN, kStats, kXform>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+}
+
+template <int kBN, bool kStats, bool kXform>
+static void conv_run(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap &mx, const CUtensorMap &mw, const ConvParams &p)
+{
+    conv_tc_kernel<kBN, kStats, kXform><<<grid, kXform ? convtc::kThreads + 128 : convtc::kThreads, smem, st>>>(mx, mw, p);
+}
+
 static int conv_launch(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout,
-                       int ksize, int dilation, const float *scale, const float *shift, const void *residual, int relu,
+                       int ksize, int dilation, const float *in_scale, const float *in_shift, int in_relu,
+                       const float *scale, const float *shift, const void *residual, int relu,
                        float *stat_part, const char *what, void *stream)
 {
     using namespace convtc;
@@ -319,20 +394,26 @@ static int conv_launch(const void *x, const void *wgt, void *out, int64_t n, int
     p.scale = scale; p.shift = shift; p.residual = static_cast<const __nv_bfloat16 *>(residual); p.relu = relu;
     p.D = static_cast<__nv_bfloat16 *>(out);
     p.stat_part = stat_part;
-    auto smem_for = [](int b, bool stats) {
-        return static_cast<size_t>(kStages) * (kTileABytes + b * kBK * 2) + 1024 + 256 + 4 * b * sizeof(float) +
+    p.in_scale = in_scale; p.in_shift = in_shift; p.in_relu = in_relu;
+    auto smem_for = [](int b, bool stats) {                      // (+64: the kXform `ready` barriers)
+        return static_cast<size_t>(kStages) * (kTileABytes + b * kBK * 2) + 1024 + 256 + 64 + 4 * b * sizeof(float) +
                (stats ? (4 * 32 * 33 + 4 * b * 2) * sizeof(float) : 0);
     };
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_for(128, false)));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_for(256, false)));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_for(128, true)));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_for(256, true)));
+        cudaError_t e = conv_configure<128, false, false>(smem_for(128, false));
+        if (e == cudaSuccess) e = conv_configure<256, false, false>(smem_for(256, false));
+        if (e == cudaSuccess) e = conv_configure<128, true, false>(smem_for(128, true));
+        if (e == cudaSuccess) e = conv_configure<256, true, false>(smem_for(256, true));
+        if (e == cudaSuccess) e = conv_configure<128, false, true>(smem_for(128, false));
+        if (e == cudaSuccess) e = conv_configure<256, false, true>(smem_for(256, false));
+        if (e == cudaSuccess) e = conv_configure<128, true, true>(smem_for(128, true));
+        if (e == cudaSuccess) e = conv_configure<256, true, true>(smem_for(256, true));
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
         configured = true;
     }
     const bool stats = stat_part != nullptr;
+    const bool xform = in_scale != nullptr || in_shift != nullptr || in_relu != 0;
     const size_t smem = smem_for(bn, stats);
     const long long tiles = static_cast<long long>(p.Nimg) * p.tiles_h * p.tiles_w * ((cout + bn - 1) / bn);
     int dev = 0, sms = kNumSMs;
@@ -340,10 +421,17 @@ static int conv_launch(const void *x, const void *wgt, void *out, int64_t n, int
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned g = static_cast<unsigned>(tiles < sms ? tiles : sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (bn == 256 && stats) conv_tc_kernel<256, true><<<g, kThreads, smem, st>>>(mx, mw, p);
-    else if (bn == 256) conv_tc_kernel<256, false><<<g, kThreads, smem, st>>>(mx, mw, p);
-    else if (stats) conv_tc_kernel<128, true><<<g, kThreads, smem, st>>>(mx, mw, p);
-    else conv_tc_kernel<128, false><<<g, kThreads, smem, st>>>(mx, mw, p);
+    const int variant = (bn == 256 ? 4 : 0) | (stats ? 2 : 0) | (xform ? 1 : 0);
+    switch (variant) {
+    case 0: conv_run<128, false, false>(g, smem, st, mx, mw, p); break;
+    case 1: conv_run<128, false, true>(g, smem, st, mx, mw, p); break;
+    case 2: conv_run<128, true, false>(g, smem, st, mx, mw, p); break;
+    case 3: conv_run<128, true, true>(g, smem, st, mx, mw, p); break;
+    case 4: conv_run<256, false, false>(g, smem, st, mx, mw, p); break;
+    case 5: conv_run<256, false, true>(g, smem, st, mx, mw, p); break;
+    case 6: conv_run<256, true, false>(g, smem, st, mx, mw, p); break;
+    default: conv_run<256, true, true>(g, smem, st, mx, mw, p); break;
+    }
     return check_launch(what);
 }
 
@@ -351,7 +439,7 @@ extern "C" int u2pl_conv_bf16_nhwc(const void *x, const void *wgt, void *out, in
                                    int64_t cout, int ksize, int dilation, const float *scale, const float *shift,
                                    const void *residual, int relu, void *stream)
 {
-    return conv_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, scale, shift, residual, relu, nullptr,
+    return conv_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, nullptr, nullptr, 0, scale, shift, residual, relu, nullptr,
                        "conv_bf16_nhwc", stream);
 }
 
@@ -366,8 +454,20 @@ extern "C" int u2pl_conv_bf16_nhwc_stats(const void *x, const void *wgt, void *o
                                          void *stream)
 {
     if (!stat_part || !sums) return bad_arg("conv_bf16_nhwc_stats: stat_part and sums are required");
-    int rc = conv_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, nullptr, nullptr, nullptr, 0, stat_part,
+    int rc = conv_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, stat_part,
                          "conv_bf16_nhwc_stats", stream);
     if (rc != 0) return rc;
+    return bn_reduce_parts(stat_part, static_cast<int>(u2pl_conv_stat_parts(n, h, w, ksize)), static_cast<int>(2 * cout), sums, stream);
+}
+
+extern "C" int u2pl_conv_bf16_nhwc_ex(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w, int64_t cin,
+                                      int64_t cout, int ksize, int dilation, const float *in_scale, const float *in_shift,
+                                      int in_relu, const float *scale, const float *shift, const void *residual, int relu,
+                                      float *stat_part, float *sums, void *stream)
+{
+    if ((stat_part == nullptr) != (sums == nullptr)) return bad_arg("conv_bf16_nhwc_ex: stat_part and sums go together");
+    int rc = conv_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, in_scale, in_shift, in_relu, scale, shift, residual, relu,
+                         stat_part, "conv_bf16_nhwc_ex", stream);
+    if (rc != 0 || !stat_part) return rc;
     return bn_reduce_parts(stat_part, static_cast<int>(u2pl_conv_stat_parts(n, h, w, ksize)), static_cast<int>(2 * cout), sums, stream);
 }

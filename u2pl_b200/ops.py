@@ -340,3 +340,30 @@ def conv_wgrad_bf16_nhwc(x, gout, dilation=1):
     _lib.check(rc, "u2pl_conv_wgrad_bf16_nhwc")
     dw = part.sum(0) if splits > 1 else part[0]
     return dw.view(3, 3, Cout, Cin).permute(2, 3, 0, 1)
+
+
+def conv_bf16_nhwc_ex(x, weight, dilation=1, in_scale=None, in_shift=None, in_relu=False, scale=None, shift=None,
+                      residual=None, relu=False, want_stats=False):
+    """General form of the implicit-GEMM convolution (u2pl_conv_bf16_nhwc_ex): optional act(x * in_scale + in_shift)
+    applied to the input inside shared memory (the previous layer's BatchNorm + ReLU), optional output epilogue, optional
+    per-channel [sum | sum of squares] of the stored output.  Returns out, or (out, sums) with want_stats."""
+    _need_cuda(x, weight, in_scale, in_shift, scale, shift, residual)
+    lib = _lib.load()
+    N, Cin, H, W = x.shape
+    Cout, k = weight.shape[0], weight.shape[2]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    assert weight.shape[1] == Cin and weight.shape[3] == k and k in (1, 3)
+    wk = weight.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape == (N, Cout, H, W) \
+            and residual.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty((N, Cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    part = sums = None
+    if want_stats:
+        part = torch.empty((int(lib.u2pl_conv_stat_parts(N, H, W, k)), 2, Cout), dtype=torch.float32, device=x.device)
+        sums = torch.empty((2, Cout), dtype=torch.float32, device=x.device)
+    rc = lib.u2pl_conv_bf16_nhwc_ex(_p(x), _p(wk), _p(out), N, H, W, Cin, Cout, k, int(dilation), _p(in_scale), _p(in_shift),
+                                    int(bool(in_relu)), _p(scale), _p(shift), _p(residual), int(bool(relu)), _p(part), _p(sums),
+                                    _stream())
+    _lib.check(rc, "u2pl_conv_bf16_nhwc_ex")
+    return (out, sums) if want_stats else out
