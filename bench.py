@@ -432,7 +432,9 @@ def our_arm(args):
                        "bank": "class-sharded, peer-mapped (U2PL_BANK_SHARDED=1)"
                                if world > 1 and os.environ.get("U2PL_BANK_SHARDED", "0") == "1" else "replicated per GPU",
                        "opt_in": {k: os.environ.get(k, "0") == "1"
-                                  for k in ("U2PL_TC_CONV", "U2PL_TC_TRAIN", "U2PL_WGRAD_STACK", "U2PL_BANK_SHARDED")}},
+                                  for k in ("U2PL_TC_CONV", "U2PL_TC_TRAIN", "U2PL_TC_CHAIN", "U2PL_TC_WGRAD", "U2PL_WGRAD_STACK",
+                                            "U2PL_BANK_SHARDED")},
+                       "infonce_depth": int(os.environ.get("U2PL_INFONCE_DEPTH", "1"))},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": 12 * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "tensor_roofline": tensor,

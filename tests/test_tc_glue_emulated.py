@@ -382,3 +382,28 @@ def test_whole_encoder_train_routing(emulated, monkeypatch):
     for name in ("encoder.layer4.2.conv2.weight", "encoder.layer3.1.conv1.weight", "encoder.layer1.0.bn1.weight", "encoder.conv1.3.weight"):
         ga, gb = res[0][1][name].grad.float(), res[1][1][name].grad.float()
         assert (ga - gb).norm() <= 0.15 * ga.norm(), (name, float((ga - gb).norm() / ga.norm()))
+
+
+def test_nograd_train_chain_routing(emulated, monkeypatch):
+    """U2PL_TC_CHAIN: the teacher's no-grad TRAIN-mode forward with the inner BatchNorm+ReLU of every bottleneck applied in
+    the next convolution's operand load -- same features, same running statistics, a third of the BN-apply passes."""
+    import copy
+    ma = _small_net().train()
+    mb = copy.deepcopy(ma)
+    x = _cl(torch.randn(2, 3, 33, 33))
+    applies, res = [], []
+    real = emulated.u2pl_bn_apply
+    monkeypatch.setattr(emulated, "u2pl_bn_apply", lambda *a: (applies.append(1), real(*a))[1])
+    for m, flag in ((ma, False), (mb, True)):
+        monkeypatch.setitem(fused.ENABLED, "tc_chain", flag)
+        n0 = len(applies)
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            feats = m.encoder(x)
+        res.append((feats, dict(m.named_buffers()), len(applies) - n0))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert (a.float() - b.float()).norm() <= 0.05 * a.float().norm()
+    for name in ("encoder.layer2.1.bn2.running_var", "encoder.layer4.0.bn1.running_mean", "encoder.layer3.2.bn3.running_var"):
+        va, vb = res[0][1][name], res[1][1][name]
+        assert (va - vb).abs().max() <= 0.03 * max(1e-3, va.abs().max().item()), name
+    assert int(res[1][1]["encoder.layer3.2.bn2.num_batches_tracked"]) == 1
+    assert res[1][2] <= res[0][2] - 2 * 14                                 # >= 14 of the 16 bottlenecks chained: 2 fewer passes each

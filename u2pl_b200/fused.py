@@ -37,7 +37,11 @@ import os
 ENABLED = {"bn": True, "wgrad": True, "tc_conv": os.environ.get("U2PL_TC_CONV", "0") == "1",
            "wgrad_stack": os.environ.get("U2PL_WGRAD_STACK", "0") == "1",
            "tc_train": os.environ.get("U2PL_TC_TRAIN", "0") == "1",
-           "tc_wgrad": os.environ.get("U2PL_TC_WGRAD", "0") == "1"}   # 3x3 stride-1 weight gradients via csrc/wgrad_tc.cu
+           "tc_wgrad": os.environ.get("U2PL_TC_WGRAD", "0") == "1",   # 3x3 stride-1 weight gradients via csrc/wgrad_tc.cu
+           # no-grad TRAIN-mode chains (the teacher's second forward, train_semi.py:362-364): conv -> BN -> ReLU -> conv with
+           # the inner BatchNorm + ReLU applied in the next convolution's operand load (conv_tc kXform), statistics from
+           # the producing convolution's epilogue: the normalised activations between the convolutions never reach HBM
+           "tc_chain": os.environ.get("U2PL_TC_CHAIN", "0") == "1"}
 
 
 def _world():
@@ -181,10 +185,19 @@ class _ConvTCFn(torch.autograd.Function):
 
 def _tc_geometry_ok(x, conv):
     k, d = conv.kernel_size[0], conv.dilation[0]
+    if type(x).__name__ == "_ShapeProxy":             # output of an eligible stride-1 conv: channels-last bf16 by construction
+        return _tc_geometry_ok(x.like, x.conv) and _geometry_only(conv)
     return (_is_cl_bf16(x) and isinstance(conv, nn.Conv2d) and conv.kernel_size in ((1, 1), (3, 3))
             and conv.stride == (1, 1) and conv.dilation == (d, d) and conv.padding == (d * (k // 2), d * (k // 2))
             and conv.groups == 1 and conv.bias is None and conv.padding_mode == "zeros"
             and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0)
+
+
+def _geometry_only(conv):
+    k, d = conv.kernel_size[0], conv.dilation[0]
+    return (isinstance(conv, nn.Conv2d) and conv.kernel_size in ((1, 1), (3, 3)) and conv.stride == (1, 1)
+            and conv.dilation == (d, d) and conv.padding == (d * (k // 2), d * (k // 2)) and conv.groups == 1
+            and conv.bias is None and conv.padding_mode == "zeros" and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0)
 
 
 def _tc_conv_ok(x, conv, bn, residual):
@@ -217,6 +230,58 @@ def conv_bn_act(x, conv, bn, relu=None, residual=None):
     _lib.check(lib.u2pl_bn_fold(C, _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), float(bn.eps),
                                 _p(scale), _p(shift), _stream()), "u2pl_bn_fold")
     return conv_bf16_nhwc(x, conv.weight, conv.dilation[0], scale, shift, residual, relu is not None and relu is not False)
+
+
+def _finalize_train_bn(bn, sums, count):
+    """Batch statistics -> (scale, shift) of a train-mode BatchNorm, with the module's side effects (running statistics,
+    num_batches_tracked, SyncBN all-reduce) -- the no-autograd half of _BNAct.forward."""
+    lib = _lib.load()
+    C = bn.num_features
+    dev = sums.device
+    if isinstance(bn, nn.SyncBatchNorm) and _world() > 1:
+        dist.all_reduce(sums)
+        count = count * _world()
+    mean, invstd = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
+    scale, shift = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
+    _lib.check(lib.u2pl_bn_finalize(_p(sums), C, ctypes.c_double(float(count)), _p(bn.weight), _p(bn.bias), _p(bn.running_mean),
+                                    _p(bn.running_var), float(bn.momentum), float(bn.eps), _p(mean), _p(invstd), _p(scale),
+                                    _p(shift), _stream()), "u2pl_bn_finalize")
+    bn.num_batches_tracked.add_(1)
+    return scale, shift
+
+
+def chain_ok(x, convs, bns, residual=None):
+    """All links of conv/BN pairs can run as one no-grad train-mode chain on the tensor-core kernel."""
+    return (ENABLED["tc_chain"] and not torch.is_grad_enabled() and all(b.training for b in bns)
+            and (residual is None or _is_cl_bf16(residual))
+            and all(type(c) in (nn.Conv2d, DilatedConv2d) and _tc_geometry_ok(x if i == 0 else _ShapeProxy(x, convs[i - 1]), c)
+                    for i, c in enumerate(convs))
+            and all(_bn_channels_ok(c.out_channels, b) for c, b in zip(convs, bns)))
+
+
+class _ShapeProxy:
+    """Stands in for the (not yet computed) channels-last bf16 output of `conv` in eligibility checks."""
+
+    def __init__(self, like, conv):
+        self.like, self.conv = like, conv
+
+
+def conv_bn_relu_chain(x, convs, bns, relu_last, residual=None):
+    """relu?(bn_k(conv_k(... relu(bn_1(conv_1(x)))))) (+ residual before the last ReLU) in train mode without autograd.
+    Link i's BatchNorm + ReLU is applied inside conv_{i+1}'s operand load; only the last BatchNorm is a separate pass
+    (its output is the block's output).  Every convolution's epilogue delivers its own batch statistics."""
+    from .ops import conv_bf16_nhwc_ex
+    lib = _lib.load()
+    in_scale = in_shift = None
+    y = x
+    for i, (conv, bn) in enumerate(zip(convs, bns)):
+        y, sums = conv_bf16_nhwc_ex(y, conv.weight, conv.dilation[0], in_scale, in_shift, i > 0, want_stats=True)
+        N, C, H, W = y.shape
+        in_scale, in_shift = _finalize_train_bn(bn, sums, N * H * W)
+    out = torch.empty_like(y)
+    _lib.check(lib.u2pl_bn_apply(_p(y), _p(residual), _p(in_scale), _p(in_shift), N * H * W, C, int(bool(relu_last)), _p(out), _stream()),
+               "u2pl_bn_apply")
+    return out
 
 
 def run_sequential(seq, x):

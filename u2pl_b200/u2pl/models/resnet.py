@@ -10,7 +10,8 @@ classes per variant, and the forward passes go through the fused BN(+ReLU+residu
 import torch
 import torch.nn as nn
 
-from u2pl_b200.fused import DilatedConv2d, StemConv2d, bn_act, conv_bn_act, run_sequential
+from u2pl_b200.fused import (DilatedConv2d, StemConv2d, bn_act, chain_ok, conv_bn_act, conv_bn_relu_chain,
+                             run_sequential)
 
 from .base import _norm
 
@@ -68,6 +69,10 @@ class _Residual(nn.Module):
 
     def forward(self, x):
         shortcut = x if self.downsample is None else run_sequential(self.downsample, x)
+        convs = [getattr(self, f"conv{i}") for i in range(1, self._depth + 1)]
+        bns = [getattr(self, f"bn{i}") for i in range(1, self._depth + 1)]
+        if chain_ok(x, convs, bns, shortcut):                   # no-grad train-mode forward (teacher T2), opt-in
+            return conv_bn_relu_chain(x, convs, bns, True, residual=shortcut)
         y = x
         for i in range(1, self._depth):
             y = conv_bn_act(y, getattr(self, f"conv{i}"), getattr(self, f"bn{i}"), self.relu)
