@@ -369,10 +369,13 @@ def our_arm(args):
         clocks.start()
     launches0 = _lib.launch_count()
     step.timers = {"entropy_partition": []}
+    if args.phases:                                          # per-phase CUDA-event brackets (analysis runs)
+        step.timers.update({name: [] for name in SemiStep.PHASES})
     ms_step, losses = timed(run_resident, args.steps)
     launches = (_lib.launch_count() - launches0) // args.steps
     torch.cuda.synchronize()
     ep_us = [a.elapsed_time(b) * 1e3 for a, b in step.timers.pop("entropy_partition")]
+    phases_ms = {k: float(np.median([a.elapsed_time(b) for a, b in v])) for k, v in step.timers.items() if v}
     step.timers = {}
     if fast:
         ms_e2e = float("nan")
@@ -438,7 +441,7 @@ def our_arm(args):
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": 12 * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "tensor_roofline": tensor,
-            "cpu_baseline": cpu, "losses": [float(x) / world for x in losses.cpu()],
+            "cpu_baseline": cpu, "phases_ms": phases_ms or None, "losses": [float(x) / world for x in losses.cpu()],
             "new_keys_last_step": int(sum(step.last.get("new_keys", [0])))}
     print(json.dumps(line))
     if world > 1:
@@ -454,6 +457,7 @@ def main():
     ap.add_argument("--workload", default="v16", choices=sorted(WORKLOADS))
     ap.add_argument("--fp32", action="store_true", help="network in fp32 (TF32 off) instead of bf16 autocast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--phases", action="store_true", help="also report median CUDA-event time per phase of the step")
     args = ap.parse_args()
     if args.impl == "reference":
         print_reference(args)

@@ -17,7 +17,7 @@ if [ "${1:-1}" = "1" ]; then
   U2PL_TC_CONV=1 timeout 300 python -m pytest tests/test_gpu_conv_tc.py -q          > $OUT/r2_pytest_conv_tc.log 2>&1;  echo "pytest conv_tc: $?"
   timeout 200 python tools/conv_bench.py                                            > $OUT/r2_conv_bench.jsonl 2>$OUT/r2_conv_bench.err; echo "conv_bench: $?"
   timeout 300 python bench.py --impl eager --steps 5 --warmup 3                     > $OUT/r2_bench_eager.json 2>$OUT/r2_bench_eager.err; echo "bench eager: $?"
-  timeout 300 python bench.py --steps 10 --warmup 3                                 > $OUT/r2_bench_n1.json 2>$OUT/r2_bench_n1.err;       echo "bench ours: $?"
+  timeout 300 python bench.py --steps 10 --warmup 3 --phases                        > $OUT/r2_bench_n1.json 2>$OUT/r2_bench_n1.err;       echo "bench ours: $?"
   U2PL_TC_CONV=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_tcconv.json 2>$OUT/r2_bench_n1_tcconv.err; echo "bench ours+tc_conv: $?"
   U2PL_TC_CONV=1 U2PL_TC_TRAIN=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_tctrain.json 2>$OUT/r2_bench_n1_tctrain.err; echo "bench ours+tc_conv+tc_train: $?"
   timeout 200 bash tools/umma_probe_sweep.sh > $OUT/r2_umma_probe.txt 2>&1; echo "umma MN-major probe: $? (0 = expected descriptor encoding confirmed)"

@@ -48,6 +48,13 @@ class SemiStep:
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
             return net(x)
 
+    PHASES = ("t1", "aug", "student_fwd", "sup_loss", "t2", "losses", "backward", "optim_ema")
+
+    def _phase(self, start, name):
+        """Close phase `name` (if it is being timed) and open the next one."""
+        self._event(start, name)
+        return self._event()
+
     def _event(self, start=None, name=None):
         """CUDA-event bracket on the current stream (only when a `timers` dict is installed, e.g. by bench.py)."""
         timers = getattr(self, "timers", None)
@@ -90,28 +97,33 @@ class SemiStep:
                     for t_p, s_p in zip(teacher.parameters(), model.parameters()):
                         t_p.data = s_p.data
             # ---- T1: pseudo labels from the eval-mode teacher (:317-324)
+            ph = self._event()
             teacher.eval()
             with torch.no_grad():
                 pred_u_teacher = self._up(self._net(teacher, image_u)["pred"], (h, w))
                 logits_u_aug, label_u_aug = torch.max(F.softmax(pred_u_teacher, dim=1), dim=1)
+            ph = self._phase(ph, "t1")
             # ---- strong augmentation (:326-337)
             if np.random.uniform(0, 1) < 0.5 and trainer["unsupervised"].get("apply_aug", False):
                 image_u_aug, label_u_aug, logits_u_aug = self.generate_unsup_data(
                     image_u, label_u_aug.clone(), logits_u_aug.clone(), mode=trainer["unsupervised"]["apply_aug"])
             else:
                 image_u_aug = image_u
+            ph = self._phase(ph, "aug")
             # ---- S: student forward on labelled + augmented unlabelled (:339-350)
             num_labeled = len(image_l)
             outs = self._net(model, torch.cat((image_l, image_u_aug)))
             pred_all, rep_all = outs["pred"], outs["rep"]
             pred_l_large = self._up(pred_all[:num_labeled], (h, w))
             pred_u_large = self._up(pred_all[num_labeled:], (h, w))
+            ph = self._phase(ph, "student_fwd")
             # ---- supervised loss (:352-358)
             if has_aux:
                 aux = self._up(outs["aux"][:num_labeled], (h, w))
                 sup_loss = self.sup_loss_fn([pred_l_large, aux], label_l.clone())
             else:
                 sup_loss = self.sup_loss_fn(pred_l_large, label_l.clone())
+            ph = self._phase(ph, "sup_loss")
             # ---- T2: train-mode teacher forward, no grad (:360-374)
             teacher.train()
             with torch.no_grad():
@@ -119,6 +131,7 @@ class SemiStep:
                 pred_all_teacher, rep_all_teacher = out_t["pred"].float().contiguous(), out_t["rep"]
                 prob_all_teacher = F.softmax(pred_all_teacher, dim=1)
                 pred_u_large_teacher = self._up(pred_all_teacher[num_labeled:], (h, w))
+            ph = self._phase(ph, "t2")
             # ---- unsupervised + contrastive losses, one entropy pass (:376-519)
             drop_percent = trainer["unsupervised"].get("drop_percent", 100)
             drop_percent = 100 - (100 - drop_percent) * (1 - epoch / trainer["epochs"])
@@ -155,9 +168,11 @@ class SemiStep:
             else:
                 contra_loss = rep_all.float().sum() * 0
 
+        ph = self._phase(ph, "losses") if epoch >= sup_only_epoch else self._event()
         loss = sup_loss + unsup_loss + contra_loss                            # :524-528
         self.optimizer.zero_grad()
         loss.backward()
+        ph = self._phase(ph, "backward")
         self.optimizer.step()
 
         if epoch >= sup_only_epoch:                                           # :531-548 EMA (parameters only)
@@ -175,6 +190,7 @@ class SemiStep:
                     torch._foreach_mul_(t_params, ema_decay)
                     torch._foreach_add_(t_params, s_params, alpha=1 - ema_decay)
 
+        self._phase(ph, "optim_ema")
         losses = torch.stack([sup_loss.detach().float(), unsup_loss.detach().float(), contra_loss.detach().float()])
         if _world_size() > 1:                                                 # :551-561, one collective, no .item()
             dist.all_reduce(losses)
