@@ -1,0 +1,79 @@
+"""CPU: the WHOLE fused training step (u2pl_b200/step.py: teacher T1, augmentation, student forward, supervised CE,
+teacher T2, fused entropy / percentiles / partition, masked CE, contrastive memory-bank loss, backward, SGD, EMA) over
+the emulated C ABI (tests/emulated_abi.py), against the CPU restatement of the reference driver step
+(oracle/step_port.py) from identical weights, inputs and RNG seeds.  fp32 network on both sides (same conv library
+here), so the three losses agree to 1e-4; the GPU counterpart is tests/test_gpu_step.py.  This is the product's host
+logic end to end -- ops.py, contra.py, bank.py, step.py, the loss_helper mirror -- running where there is no GPU."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import bench
+import emulated_abi
+from oracle import model_port, step_port
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    from u2pl_b200 import contra
+    fake = emulated_abi.install(monkeypatch)
+    yield fake
+    contra.forget_banks()
+
+
+def test_semi_step_on_emulated_abi_matches_reference_step(emulated):
+    import u2pl_b200
+    u2pl_b200.install()
+    from u2pl.models.model_helper import ModelBuilder
+    from u2pl.utils.loss_helper import get_criterion
+    from u2pl.utils.lr_helper import get_optimizer
+    from u2pl_b200 import contra
+    from u2pl_b200.step import SemiStep
+
+    C, crop, bl, bu = 21, 65, 2, 2
+    cfg = bench.make_cfg("tiny")
+    cfg["net"]["encoder"]["type"] = "u2pl.models.resnet.resnet50"
+    torch.manual_seed(3)
+    model = ModelBuilder(copy.deepcopy(cfg["net"]))
+    with torch.no_grad():
+        model.decoder.classifier[-1].weight.mul_(8.0)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.p = 0.0
+    teacher = copy.deepcopy(model)
+    ref = step_port.ReferenceStep(model_port.state_from_module(model), model_port.state_from_module(teacher), cfg, "resnet50")
+    ref.student.dropout_p = ref.teacher.dropout_p = 0.0
+    for p in teacher.parameters():
+        p.requires_grad = False
+    lr = 0.001
+    opt = get_optimizer([dict(params=model.encoder.parameters(), lr=lr),
+                         dict(params=model.decoder.parameters(), lr=lr * 10)], cfg["trainer"]["optimizer"])
+    memobank = [[torch.zeros(0, 256)] for _ in range(C)]
+    ptrs = [torch.zeros(1, dtype=torch.long) for _ in range(C)]
+    qsize = [30000] * C
+    qsize[0] = 50000
+    step = SemiStep(model, teacher, opt, get_criterion(cfg), cfg, memobank, ptrs, qsize, amp=False, channels_last=False)
+
+    got, want = [], []
+    for rnd, (seed_np, seed_t) in enumerate([(5, 6), (7, 8)]):
+        image_l, label_l, image_u = bench.synth_batch(100 + rnd, bl, bu, crop, C)
+        np.random.seed(seed_np)
+        torch.manual_seed(seed_t)
+        want.append(ref.step(image_l, label_l, image_u, 40, 4000 + rnd, 100))
+        np.random.seed(seed_np)
+        torch.manual_seed(seed_t)
+        losses = step(image_l, label_l, image_u, 40, 4000 + rnd, 100)
+        got.append([float(x) for x in losses])
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (got, want)
+    assert want[1][2] > 0 and got[1][2] > 0                      # the contrastive branch really ran in step 2
+    bank = contra.bank_for(memobank, qsize, 256, torch.device("cpu"))
+    for c in range(C):                                           # same keys in the same FIFO order (to fp32 noise of step-2 weights)
+        a, b = bank.materialize(c).numpy(), ref.memobank[c][0]
+        assert a.shape == b.shape and np.allclose(a, b, atol=1e-4), c
+    k = "decoder.classifier.8.weight"
+    assert (dict(teacher.named_parameters())[k].detach() - ref.teacher.s[k].detach()).abs().max() <= 1e-5     # EMA
+    assert (dict(model.named_parameters())[k].detach() - ref.student.s[k].detach()).abs().max() <= 1e-4       # SGD

@@ -6,167 +6,18 @@ libu2pl_b200.so would, reinterprets the host memory exactly as the header docume
 checked against CPU loops on the GPU (tools/cu/tc_selftest.cu); what this pins is the layer in between -- argument
 order, physical layouts, permutes, autograd plumbing -- which otherwise only a GPU run would exercise.
 Nothing here is a product path: the product has no CPU fallback, the emulation exists only inside this test."""
-import ctypes
-
-import numpy as np
 import pytest
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from u2pl_b200 import _lib, fused, ops
-
-
-def _addr(p):
-    return p.value if isinstance(p, ctypes.c_void_p) else (int(p) if p is not None else None)
-
-
-def _view(p, shape, dtype):
-    """Host memory at pointer p as a torch tensor (bf16 through its uint16 bit pattern)."""
-    a = _addr(p)
-    if a is None:
-        return None
-    n = int(np.prod(shape))
-    if dtype is torch.bfloat16:
-        arr = np.ctypeslib.as_array((ctypes.c_uint16 * n).from_address(a))
-        return torch.from_numpy(arr).view(torch.bfloat16).view(*shape)
-    arr = np.ctypeslib.as_array((ctypes.c_float * n).from_address(a))
-    return torch.from_numpy(arr).view(*shape)
-
-
-class FakeLib:
-    """Semantics of include/u2pl_b200.h for the entry points the glue under test calls."""
-
-    def u2pl_conv_bf16_nhwc(self, x, w, out, n, h, wd, cin, cout, k, d, scale, shift, res, relu, stream):
-        xt = _view(x, (n, h, wd, cin), torch.bfloat16).float().permute(0, 3, 1, 2)
-        wt = _view(w, (cout, k, k, cin), torch.bfloat16).float().permute(0, 3, 1, 2)
-        y = F.conv2d(xt, wt, None, 1, d * (k // 2), d)
-        if _addr(scale) is not None:
-            y = y * _view(scale, (cout,), torch.float32)[None, :, None, None]
-        if _addr(shift) is not None:
-            y = y + _view(shift, (cout,), torch.float32)[None, :, None, None]
-        if _addr(res) is not None:
-            y = y + _view(res, (n, h, wd, cout), torch.bfloat16).float().permute(0, 3, 1, 2)
-        if relu:
-            y = F.relu(y)
-        _view(out, (n, h, wd, cout), torch.bfloat16).copy_(y.permute(0, 2, 3, 1).bfloat16())
-        return 0
-
-    def u2pl_conv_bf16_nhwc_ex(self, x, w, out, n, h, wd, cin, cout, k, d, in_scale, in_shift, in_relu, scale, shift, res, relu,
-                               part, sums, stream):
-        xt = _view(x, (n, h, wd, cin), torch.bfloat16).float()
-        if _addr(in_scale) is not None:
-            xt = xt * _view(in_scale, (cin,), torch.float32)
-        if _addr(in_shift) is not None:
-            xt = xt + _view(in_shift, (cin,), torch.float32)
-        z = (F.relu(xt) if in_relu else xt).bfloat16().contiguous()      # the kernel rewrites the tile in bf16
-        rc = self.u2pl_conv_bf16_nhwc(ctypes.c_void_p(z.data_ptr()), w, out, n, h, wd, cin, cout, k, d, scale, shift, res, relu, stream)
-        if _addr(sums) is not None:
-            y = _view(out, (n * h * wd, cout), torch.bfloat16).float()
-            _view(sums, (2, cout), torch.float32).copy_(torch.stack([y.sum(0), (y * y).sum(0)]))
-        return rc
-
-    def u2pl_conv_stat_parts(self, n, h, w, k):
-        return (n * h * w + 127) // 128 if k == 1 else n * ((h + 7) // 8) * ((w + 15) // 16)
-
-    def u2pl_conv_bf16_nhwc_stats(self, x, w, out, n, h, wd, cin, cout, k, d, part, sums, stream):
-        self.u2pl_conv_bf16_nhwc(x, w, out, n, h, wd, cin, cout, k, d, None, None, None, 0, stream)
-        y = _view(out, (n * h * wd, cout), torch.bfloat16).float()
-        _view(sums, (2, cout), torch.float32).copy_(torch.stack([y.sum(0), (y * y).sum(0)]))
-        return 0
-
-    def u2pl_conv_wgrad_splits(self, n, h, w, cin, cout):
-        return 3
-
-    def u2pl_conv_wgrad_bf16_nhwc(self, x, g, part, n, h, wd, cin, cout, d, stream):
-        xt = _view(x, (n, h, wd, cin), torch.bfloat16).float().permute(0, 3, 1, 2)
-        gt = _view(g, (n, h, wd, cout), torch.bfloat16).float().permute(0, 3, 1, 2)
-        with torch.enable_grad():                                          # (this fake may run inside an autograd backward)
-            wz = torch.zeros(cout, cin, 3, 3, requires_grad=True)
-            F.conv2d(xt, wz, None, 1, d, d).backward(gt)
-        dw = wz.grad.permute(2, 3, 0, 1).reshape(9, cout, cin)           # [tap][co][ci]
-        p = _view(part, (3, 9, cout, cin), torch.float32)
-        p[0].copy_(dw * 0.5); p[1].copy_(dw * 0.25); p[2].copy_(dw * 0.25)   # the caller must sum the splits
-        return 0
-
-    def u2pl_bn_fold(self, C, gamma, beta, mean, var, eps, scale, shift, stream):
-        g, b = _view(gamma, (C,), torch.float32), _view(beta, (C,), torch.float32)
-        m, v = _view(mean, (C,), torch.float32), _view(var, (C,), torch.float32)
-        s = g / torch.sqrt(v + eps)
-        _view(scale, (C,), torch.float32).copy_(s)
-        _view(shift, (C,), torch.float32).copy_(b - m * s)
-        return 0
-
-    # ---- csrc/bn.cu entry points (x / y / dy / residual: [M, C] bf16 rows = channels-last pixels)
-    def u2pl_bn_parts(self):
-        return 4
-
-    def u2pl_bn_stats(self, x, M, C, partial, sums, stream):
-        xv = _view(x, (M, C), torch.bfloat16).float()
-        _view(sums, (2, C), torch.float32).copy_(torch.stack([xv.sum(0), (xv * xv).sum(0)]))
-        return 0
-
-    def u2pl_bn_finalize(self, sums, C, count, gamma, beta, rmean, rvar, momentum, eps, mean, invstd, scale, shift, stream):
-        n = count.value if hasattr(count, "value") else float(count)
-        sm = _view(sums, (2, C), torch.float32).double()
-        mu = sm[0] / n
-        var = (sm[1] / n - mu * mu).clamp_min(0)
-        inv = 1.0 / torch.sqrt(var + eps)
-        g, b = _view(gamma, (C,), torch.float32).double(), _view(beta, (C,), torch.float32).double()
-        _view(mean, (C,), torch.float32).copy_(mu.float())
-        _view(invstd, (C,), torch.float32).copy_(inv.float())
-        _view(scale, (C,), torch.float32).copy_((g * inv).float())
-        _view(shift, (C,), torch.float32).copy_((b - mu * g * inv).float())
-        rm, rv = _view(rmean, (C,), torch.float32), _view(rvar, (C,), torch.float32)
-        rm.mul_(1 - momentum).add_(momentum * mu.float())
-        rv.mul_(1 - momentum).add_(momentum * (var * n / (n - 1)).float())
-        return 0
-
-    def u2pl_bn_apply(self, x, res, scale, shift, M, C, relu, y, stream):
-        v = _view(x, (M, C), torch.bfloat16).float() * _view(scale, (C,), torch.float32) + _view(shift, (C,), torch.float32)
-        if _addr(res) is not None:
-            v = v + _view(res, (M, C), torch.bfloat16).float()
-        _view(y, (M, C), torch.bfloat16).copy_((F.relu(v) if relu else v).bfloat16())
-        return 0
-
-    @staticmethod
-    def _masked(dy, y, M, C):
-        g = _view(dy, (M, C), torch.bfloat16).float()
-        return g * (_view(y, (M, C), torch.bfloat16).float() > 0) if _addr(y) is not None else g
-
-    def u2pl_bn_backward_reduce(self, dy, x, y, mean, invstd, M, C, partial, sums, stream):
-        g = self._masked(dy, y, M, C)
-        xh = (_view(x, (M, C), torch.bfloat16).float() - _view(mean, (C,), torch.float32)) * _view(invstd, (C,), torch.float32)
-        _view(sums, (2, C), torch.float32).copy_(torch.stack([g.sum(0), (g * xh).sum(0)]))
-        return 0
-
-    def u2pl_bn_backward_elemt(self, dy, x, y, mean, invstd, gamma, sums, count, M, C, coef, dx, dres, stream):
-        n = count.value if hasattr(count, "value") else float(count)
-        g = self._masked(dy, y, M, C)
-        sm = _view(sums, (2, C), torch.float32)
-        inv, mu, ga = _view(invstd, (C,), torch.float32), _view(mean, (C,), torch.float32), _view(gamma, (C,), torch.float32)
-        A = ga * inv
-        B = -ga * inv * inv * sm[1] / n
-        D = -A * sm[0] / n - B * mu
-        _view(dx, (M, C), torch.bfloat16).copy_((A * g + B * _view(x, (M, C), torch.bfloat16).float() + D).bfloat16())
-        if _addr(dres) is not None:
-            _view(dres, (M, C), torch.bfloat16).copy_(g.bfloat16())
-        return 0
-
-    def u2pl_last_error(self):
-        return b""
+import emulated_abi
+from u2pl_b200 import fused, ops
 
 
 @pytest.fixture
 def emulated(monkeypatch):
-    fake = FakeLib()
-    monkeypatch.setattr(_lib, "load", lambda *a, **k: fake)
-    monkeypatch.setattr(ops, "_need_cuda", lambda *ts: None)
-    monkeypatch.setattr(ops, "_stream", lambda: None)
-    monkeypatch.setattr(fused, "_stream", lambda: None)
-    monkeypatch.setattr(fused, "_is_cl_bf16", lambda x: x.dtype == torch.bfloat16 and x.dim() == 4
-                        and x.is_contiguous(memory_format=torch.channels_last))
-    return fake
+    return emulated_abi.install(monkeypatch)
 
 
 def _cl(t):
