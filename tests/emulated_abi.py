@@ -347,6 +347,26 @@ class FakeLoss:
                 _arr(bwd_scale, 1, ctypes.c_float)[0] = up * total / n / n if n else np.nan
         return 0
 
+    def u2pl_ohem_select(self, logits, target, B, C, HW, ignore, thresh, min_kept, new_target, kth_value, n_valid, ws, ws_bytes, stream):
+        x = _arr(logits, B * C * HW, ctypes.c_float).reshape(B, C, HW)
+        t = _arr(target, B * HW, ctypes.c_int64).reshape(-1)
+        valid = t != ignore
+        nv = int(valid.sum())
+        keep = valid.copy()
+        kth = np.float32(np.nan)
+        if nv > 0 and min_kept <= nv:                                       # loss_helper.py:512-526
+            prob = port.softmax(x).transpose(1, 0, 2).reshape(C, -1)
+            mp = np.where(valid, prob[np.where(valid, t, 0), np.arange(t.size)], np.float32(1))
+            th = np.float32(thresh)
+            if min_kept > 0:
+                kth = np.sort(mp, kind="stable")[min(mp.size, min_kept) - 1]
+                th = max(th, kth)
+                keep = valid & (mp <= th)
+        _arr(new_target, B * HW, ctypes.c_int64)[:] = np.where(keep, t, ignore)
+        _arr(kth_value, 1, ctypes.c_float)[0] = kth
+        _arr(n_valid, 1, ctypes.c_int64)[0] = nv
+        return 0
+
     def u2pl_contra_prep_lowres(self, label_l, label_u, entropy, thresh, lo_idx, hi_idx, Bl, Bu, H, W, h, w, C, ignore, neg_high,
                                 bits, low, high, stream):
         ll = _arr(label_l, Bl * H * W, ctypes.c_int64).reshape(Bl, H, W)

@@ -77,3 +77,29 @@ def test_semi_step_on_emulated_abi_matches_reference_step(emulated):
     k = "decoder.classifier.8.weight"
     assert (dict(teacher.named_parameters())[k].detach() - ref.teacher.s[k].detach()).abs().max() <= 1e-5     # EMA
     assert (dict(model.named_parameters())[k].detach() - ref.student.s[k].detach()).abs().max() <= 1e-4       # SGD
+
+
+@pytest.mark.parametrize("min_kept", [50, 100000])
+def test_ohem_criterion_with_aux_on_emulated_abi(emulated, min_kept):
+    """get_criterion -> CriterionOhem (Cityscapes configs: ohem + aux head, loss_helper.py:323-360, 451-531) through
+    ops.ohem_select / cross_entropy_mean, forward and gradient, against the oracle's ohem_ce."""
+    import u2pl_b200
+    from oracle import port
+    u2pl_b200.install()
+    from u2pl.utils.loss_helper import get_criterion
+    crit = get_criterion({"criterion": {"type": "ohem", "kwargs": {"thresh": 0.7, "min_kept": min_kept}},
+                          "net": {"aux_loss": {"loss_weight": 0.4, "aux_plane": 1024}}, "dataset": {"ignore_label": 255}})
+    g = torch.Generator().manual_seed(min_kept)
+    main = (torch.randn(2, 19, 13, 11, generator=g) * 3).requires_grad_(True)
+    aux = (torch.randn(2, 19, 13, 11, generator=g) * 3).requires_grad_(True)
+    target = torch.randint(0, 19, (2, 13, 11), generator=g)
+    target[:, :2] = 255
+    loss = crit([main, aux], target)
+    loss.backward()
+    l_main, kept_main = port.ohem_ce(main.detach().numpy(), target.numpy(), 0.7, min_kept)
+    l_aux, _ = port.ohem_ce(aux.detach().numpy(), target.numpy(), 0.7, min_kept)
+    assert abs(float(loss.detach()) - (float(l_main) + 0.4 * float(l_aux))) <= 1e-5
+    mr = main.detach().clone().requires_grad_(True)
+    t_kept = torch.where(torch.from_numpy(kept_main), target, torch.full_like(target, 255))
+    torch.nn.functional.cross_entropy(mr, t_kept, ignore_index=255).backward()
+    assert (main.grad - mr.grad).abs().max() <= 1e-6
