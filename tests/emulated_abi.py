@@ -390,7 +390,64 @@ class FakeLoss:
         return 0
 
 
-class FakeAll(FakeTC, FakeContra, FakeLoss):
+class FakeShards:
+    """u2pl_shard_alloc / open / close with POSIX shared memory standing in for CUDA IPC: the 64-byte handle carries the
+    segment name, a peer process maps the same bytes.  Plus the sharded InfoNCE entry point, which reads each active
+    class's negatives through its own base pointer."""
+
+    def __init__(self):
+        self._segments = {}
+
+    def u2pl_shard_alloc(self, nbytes, dptr, handle64):
+        from multiprocessing import shared_memory
+        seg = shared_memory.SharedMemory(create=True, size=int(nbytes))
+        np.frombuffer(seg.buf, dtype=np.uint8)[:] = 0
+        addr = ctypes.addressof(ctypes.c_char.from_buffer(seg.buf))
+        self._segments[addr] = seg
+        dptr._obj.value = addr                                     # ctypes.byref(c_void_p)
+        name = seg.name.encode()
+        ctypes.memmove(handle64, name + b"\0" * (64 - len(name)), 64)
+        return 0
+
+    def u2pl_shard_open(self, handle64, dptr):
+        from multiprocessing import shared_memory
+        name = bytes(handle64).split(b"\0")[0].decode()
+        seg = shared_memory.SharedMemory(name=name)
+        addr = ctypes.addressof(ctypes.c_char.from_buffer(seg.buf))
+        self._segments[addr] = seg
+        dptr._obj.value = addr
+        return 0
+
+    def u2pl_shard_close(self, ptr, owned):
+        seg = self._segments.pop(_addr(ptr) if not isinstance(ptr, int) else ptr, None)
+        if seg is not None:
+            try:
+                seg.close()
+                if owned:
+                    seg.unlink()
+            except (BufferError, FileNotFoundError):
+                pass
+        return 0
+
+    def u2pl_infonce_forward_sharded(self, rep, sn, sd, sp, P, D, hw, an_bits, blockoff_an, act_class, a_ord, neg_rows, proto,
+                                     class_bank, nact, nq, nneg, temp, valid_seg, loss_q, grad_rows, anchor_pix, loss, stream):
+        bases = _arr(class_bank, nact, ctypes.c_int64)
+        nr = _arr(neg_rows, nact * nq * nneg, ctypes.c_int32).reshape(nact, nq, nneg).astype(np.int64)
+        # gather every active class's rows from its own shard into one temporary bank, then reuse the replicated-bank maths
+        tmp = np.zeros((nact * nq * nneg, D), np.float32)
+        remap = np.arange(nact * nq * nneg, dtype=np.int32).reshape(nact, nq, nneg)
+        for a in range(nact):
+            shard = _arr(int(bases[a]), (int(nr[a].max()) + 1) * D, ctypes.c_float).reshape(-1, D)
+            tmp[remap[a].ravel()] = shard[nr[a].ravel()]
+        return self.u2pl_infonce_forward(rep, sn, sd, sp, P, D, hw, an_bits, blockoff_an, act_class, a_ord,
+                                         ctypes.c_void_p(remap.ctypes.data), proto, ctypes.c_void_p(tmp.ctypes.data), nact, nq, nneg,
+                                         temp, valid_seg, loss_q, grad_rows, anchor_pix, loss, stream)
+
+
+class FakeAll(FakeTC, FakeContra, FakeLoss, FakeShards):
+    def __init__(self):
+        FakeShards.__init__(self)
+
     def u2pl_last_error(self):
         return b""
 
@@ -398,9 +455,23 @@ class FakeAll(FakeTC, FakeContra, FakeLoss):
         return 0
 
 
+class DirectPatcher:
+    """monkeypatch stand-in for spawned worker processes (nothing to undo there)."""
+
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+
+def _host_tensor_from_ptr(ptr, shape, device=None):
+    n = int(np.prod(shape))
+    return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * n).from_address(int(ptr)))).view(*shape)
+
+
 def install(monkeypatch, fake=None):
     """Route u2pl_b200's ctypes layer to the emulation and lift its CUDA-only guards (monkeypatch scope)."""
-    from u2pl_b200 import _lib, contra, fused, ops
+    from u2pl_b200 import _lib, bank, contra, fused, ops
+    monkeypatch.setattr(bank, "_tensor_from_ptr", _host_tensor_from_ptr)
     fake = fake or FakeAll()
     monkeypatch.setattr(_lib, "load", lambda *a, **k: fake)
     for mod in (ops, contra):

@@ -117,3 +117,69 @@ def test_two_rank_sharded_bank_protocol():
         ret = mgr.dict()
         mp.spawn(_sharded_worker, args=(world, 31000 + os.getpid() % 2000, ret), nprocs=world, join=True)
         assert ret.get(0) and ret.get(1)
+
+
+# ------------------------------------------------------------------ contra.py, world 2, replicated vs class-sharded bank
+def _contra_worker(rank, world, port_no, sharded, ret):
+    """compute_contra_memobank_loss on two gloo ranks over the emulated C ABI (tests/emulated_abi.py; CUDA IPC is stood in
+    for by POSIX shared memory): the CPU analogue of tests/test_gpu_sharded_bank.py."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emulated_abi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    os.environ["U2PL_BANK_SHARDED"] = "1" if sharded else "0"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    emulated_abi.install(emulated_abi.DirectPatcher())
+    from u2pl_b200 import bank as bank_mod, contra
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "contra_c21.npz"))
+    cfg = {k: v for k, v in zip(g["cfg_keys"].tolist(), g["cfg_vals"].tolist())}
+    for k in ("low_rank", "high_rank", "num_negatives", "num_queries"):
+        cfg[k] = int(cfg[k])
+    C, D = g["s0_label_l"].shape[1], g["s0_rep"].shape[1]
+    qsize = g["queue_size"].tolist()
+    memobank = [[torch.zeros(0, D)] for _ in range(C)]
+    ptrs = [torch.zeros(1, dtype=torch.long) for _ in range(C)]
+    steps = int(g["steps"])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))                                 # noqa: E731
+    out = {"loss": [], "grad": [], "keys": []}
+    for it in range(steps):
+        s = (it + rank) % steps
+        rep = t(g[f"s{s}_rep"]).requires_grad_(True)
+        args = [t(g[f"s{s}_label_l"].astype(np.int64)), t(g[f"s{s}_label_u"].astype(np.int64)), t(g[f"s{s}_prob_l"]), t(g[f"s{s}_prob_u"]),
+                t(g[f"s{s}_low_mask"].astype(np.float32)), t(g[f"s{s}_high_mask"].astype(np.float32))]
+        torch.manual_seed(500 + 10 * it + rank)
+        new_keys, loss = contra.compute_contra_memobank_loss(rep, *args, cfg, memobank, ptrs, qsize, t(g[f"s{s}_rep_teacher"]))
+        loss.backward()
+        out["loss"].append(float(loss.detach()))
+        out["grad"].append(rep.grad.numpy().copy() if rep.grad is not None else None)
+        out["keys"].append(list(new_keys))
+    bank = contra.bank_for(memobank, qsize, D, torch.device("cpu"))
+    assert isinstance(bank, bank_mod.ShardedBank) == bool(sharded)
+    dist.barrier()
+    out["bank"] = [bank.materialize(c).numpy().copy() for c in range(C)]
+    out["owned"] = [bank.owns(c) for c in range(C)] if sharded else None
+    dist.barrier()
+    ret[(rank, sharded)] = out
+    if sharded:
+        bank.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_contra_sharded_equals_replicated():
+    world = 2
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        for i, sharded in enumerate((False, True)):
+            mp.spawn(_contra_worker, args=(world, 35000 + 11 * i + os.getpid() % 1500, sharded, ret), nprocs=world, join=True)
+        for rank in range(world):
+            a, b = ret[(rank, False)], ret[(rank, True)]
+            assert a["keys"] == b["keys"] and any(x > 0 for x in a["loss"])
+            assert a["loss"] == b["loss"], (a["loss"], b["loss"])                           # same rows, same maths
+            for ga, gb in zip(a["grad"], b["grad"]):
+                assert (ga is None) == (gb is None) and (ga is None or np.array_equal(ga, gb))
+            for ca, cb in zip(a["bank"], b["bank"]):
+                assert np.array_equal(ca, cb)
+        assert ret[(0, True)]["owned"] == [c % 2 == 0 for c in range(len(ret[(0, True)]["owned"]))]
+        for c in range(len(ret[(0, True)]["bank"])):
+            assert np.array_equal(ret[(0, True)]["bank"][c], ret[(1, True)]["bank"][c])     # every rank sees the same bank

@@ -116,6 +116,14 @@ class _DevicePtrView:
                                          "strides": None}
 
 
+def _tensor_from_ptr(ptr, shape, device=None):
+    """Zero-copy fp32 tensor over raw device memory.  With `device` (the pointer's own device) nothing is copied; without it
+    torch places the tensor on whatever device owns the pointer (a mapped peer shard lives on the peer's device)."""
+    import torch
+    view = _DevicePtrView(ptr, shape)
+    return torch.as_tensor(view, device=device) if device is not None else torch.as_tensor(view)
+
+
 class ShardedBank:
     """Banks sharded BY CLASS over the GPUs of one box: rank c % world holds class c's ring in a cudaMalloc'd shard
     that every other rank maps through CUDA IPC.  Ring bookkeeping (host integers) is replicated for all classes --
@@ -157,7 +165,7 @@ class ShardedBank:
             self.base.append(int(peer.value))
         self.device = device
         # the local shard as a tensor (what u2pl_bank_append writes; same device, so as_tensor does not copy)
-        self.rows = torch.as_tensor(_DevicePtrView(self.base[rank], (max(shard_rows[rank], 1), self.dim)), device=device)
+        self.rows = _tensor_from_ptr(self.base[rank], (max(shard_rows[rank], 1), self.dim), device)
         self._flag = torch.zeros(1, dtype=torch.int32, device=device)
 
     def owns(self, c):
@@ -181,7 +189,7 @@ class ShardedBank:
         if o == self.rank:
             shard = self.rows
         else:       # torch places a tensor built from a mapped peer pointer on the peer's device: copy the ring's rows over
-            peer = torch.as_tensor(_DevicePtrView(self.base[o], (max(self.shard_rows[o], 1), self.dim)))
+            peer = _tensor_from_ptr(self.base[o], (max(self.shard_rows[o], 1), self.dim))
             shard = torch.empty((r.cap, self.dim), dtype=torch.float32, device=self.device)
             shard.copy_(peer[r.row_base:r.row_base + r.cap])
             idx = (r.start + torch.arange(r.length, device=self.device)) % r.cap

@@ -167,7 +167,7 @@ def _prepare(rep, label_bits, prob_l, prob_u, low_mask, high_mask, cfg, memobank
     rank, world = _world()
     if world > 1:                                       # one collective instead of C barriers + object gathers
         all_tot = torch.empty((world, 3, C), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(all_tot, totals)
+        dist.all_gather_into_tensor(all_tot.view(-1), totals.view(-1))   # flat: the same call is valid on NCCL and gloo
     else:
         all_tot = totals[None]
     tot = all_tot.cpu().numpy().astype(np.int64)        # the step's single device->host sync on this path
