@@ -435,7 +435,7 @@ def our_arm(args):
                        "bank": "class-sharded, peer-mapped (U2PL_BANK_SHARDED=1)"
                                if world > 1 and os.environ.get("U2PL_BANK_SHARDED", "0") == "1" else "replicated per GPU",
                        "opt_in": {k: os.environ.get(k, "0") == "1"
-                                  for k in ("U2PL_TC_CONV", "U2PL_TC_TRAIN", "U2PL_TC_CHAIN", "U2PL_TC_WGRAD", "U2PL_WGRAD_STACK",
+                                  for k in ("U2PL_TC_CONV", "U2PL_TC_TRAIN", "U2PL_TC_CHAIN", "U2PL_TC_WGRAD", "U2PL_POOL", "U2PL_WGRAD_STACK",
                                             "U2PL_BANK_SHARDED")},
                        "infonce_depth": int(os.environ.get("U2PL_INFONCE_DEPTH", "1"))},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,

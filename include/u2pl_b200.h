@@ -265,6 +265,17 @@ int u2pl_bn_backward_elemt(const void *dy, const void *x, const void *y, const f
                            float *coef /* scratch [3][C] */, void *dx, void *dres, void *stream);
 
 /* ------------------------------------------------------------------------
+ * A1  stem max-pooling: nn.MaxPool2d(kernel_size=3, stride=2, padding=1, ceil_mode=True) (resnet.py:185,282) on a
+ *     channels-last bf16 tensor.  x [n,h,w,c] -> y [n,ho,wo,c] with ho = u2pl_maxpool3s2_out(h); tap [n,ho,wo,c] uint8 =
+ *     winning window position kh*3+kw (ATen's tie rule: row-major scan, a later tap wins only if strictly greater or
+ *     NaN), may be NULL when no backward follows.  backward: dx[n,h,w,c] = sum of dy over the windows whose tap points
+ *     at (h,w) -- a gather, no atomics.  c % 8 == 0.
+ * ---------------------------------------------------------------------- */
+int64_t u2pl_maxpool3s2_out(int64_t n);
+int u2pl_maxpool3s2_forward(const void *x, void *y, void *tap, int64_t n, int64_t h, int64_t w, int64_t c, void *stream);
+int u2pl_maxpool3s2_backward(const void *dy, const void *tap, void *dx, int64_t n, int64_t h, int64_t w, int64_t c, void *stream);
+
+/* ------------------------------------------------------------------------
  * A1  1x1 convolution as a tensor-core GEMM (tcgen05 + TMA), optional folded-BN + ReLU epilogue
  * replaces: conv1x1 (resnet.py:39-41) [+ eval-mode BatchNorm + ReLU] on channels-last activations.
  *   D[M,N] = act( (A[M,K] . B[N,K]^T) * scale[n] + shift[n] ),  A/B/D bf16 row-major, fp32 accumulation;

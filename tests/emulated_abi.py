@@ -444,7 +444,40 @@ class FakeShards:
                                          temp, valid_seg, loss_q, grad_rows, anchor_pix, loss, stream)
 
 
-class FakeAll(FakeTC, FakeContra, FakeLoss, FakeShards):
+class FakePool:
+    """csrc/pool.cu: 3x3 / stride 2 / pad 1 / ceil_mode max-pooling of [n,h,w,c] bf16 with a uint8 tap map."""
+
+    def u2pl_maxpool3s2_out(self, n):
+        return F.max_pool2d(torch.zeros(1, 1, n, n), 3, 2, 1, ceil_mode=True).shape[-1]
+
+    def u2pl_maxpool3s2_forward(self, x, y, tap, n, h, w, c, stream):
+        xt = _view(x, (n, h, w, c), torch.bfloat16).float().permute(0, 3, 1, 2)
+        out, idx = F.max_pool2d(xt, 3, 2, 1, ceil_mode=True, return_indices=True)          # idx: flat h*W + w in the input plane
+        ho, wo = out.shape[2:]
+        _view(y, (n, ho, wo, c), torch.bfloat16).copy_(out.permute(0, 2, 3, 1).bfloat16())
+        if _addr(tap) is not None:
+            ih, iw = idx // w, idx % w
+            kh = ih - (2 * torch.arange(ho).view(1, 1, ho, 1) - 1)
+            kw = iw - (2 * torch.arange(wo).view(1, 1, 1, wo) - 1)
+            t = (kh * 3 + kw).permute(0, 2, 3, 1).to(torch.uint8).contiguous()
+            _arr(tap, n * ho * wo * c, ctypes.c_uint8)[:] = t.numpy().ravel()
+        return 0
+
+    def u2pl_maxpool3s2_backward(self, dy, tap, dx, n, h, w, c, stream):
+        ho, wo = self.u2pl_maxpool3s2_out(h), self.u2pl_maxpool3s2_out(w)
+        g = _view(dy, (n, ho, wo, c), torch.bfloat16).float()
+        t = torch.from_numpy(_arr(tap, n * ho * wo * c, ctypes.c_uint8).reshape(n, ho, wo, c).astype(np.int64))
+        out = torch.zeros(n, h, w, c)
+        hh = (2 * torch.arange(ho).view(1, ho, 1, 1) - 1) + t // 3
+        ww = (2 * torch.arange(wo).view(1, 1, wo, 1) - 1) + t % 3
+        nn_ = torch.arange(n).view(n, 1, 1, 1).expand_as(t)
+        cc = torch.arange(c).view(1, 1, 1, c).expand_as(t)
+        out.index_put_((nn_, hh, ww, cc), g, accumulate=True)
+        _view(dx, (n, h, w, c), torch.bfloat16).copy_(out.bfloat16())
+        return 0
+
+
+class FakeAll(FakeTC, FakeContra, FakeLoss, FakeShards, FakePool):
     def __init__(self):
         FakeShards.__init__(self)
 

@@ -157,3 +157,31 @@ def test_wgrad_addressing_model(N, Cin, H, W, Cout, d, splits):
     y.backward(go)
     got = wgrad_model(x.permute(0, 2, 3, 1).contiguous().numpy(), go.permute(0, 2, 3, 1).contiguous().numpy(), d, splits)
     assert np.abs(got - w.grad.numpy()).max() <= 2e-4 * max(1.0, float(w.grad.abs().max()))
+
+
+# ------------------------------------------------------------------ csrc/pool.cu: scan order and tie rule vs ATen
+def test_maxpool_tap_rule_matches_aten():
+    """Forward kernel's rule -- windows scanned kh then kw over in-bounds taps, first tap initialises, a later tap wins only
+    if strictly greater -- gives the same argmax as ATen (return_indices) on inputs full of ties."""
+    g = torch.Generator().manual_seed(0)
+    x = (F.relu(torch.randn(2, 3, 11, 14, generator=g)) * 4).round() / 4           # few distinct values: many ties
+    out, idx = F.max_pool2d(x, 3, 2, 1, ceil_mode=True, return_indices=True)
+    N, C, H, W = x.shape
+    Ho, Wo = out.shape[2:]
+    for n in range(N):
+        for c in range(C):
+            for ho in range(Ho):
+                for wo in range(Wo):
+                    best, tap = None, None
+                    for kh in range(3):
+                        h = 2 * ho - 1 + kh
+                        if not 0 <= h < H:
+                            continue
+                        for kw in range(3):
+                            w = 2 * wo - 1 + kw
+                            if not 0 <= w < W:
+                                continue
+                            v = float(x[n, c, h, w])
+                            if tap is None or v > best:
+                                best, tap = v, (h, w)
+                    assert best == float(out[n, c, ho, wo]) and tap[0] * W + tap[1] == int(idx[n, c, ho, wo])

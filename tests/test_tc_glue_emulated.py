@@ -258,3 +258,25 @@ def test_nograd_train_chain_routing(emulated, monkeypatch):
         assert (va - vb).abs().max() <= 0.03 * max(1e-3, va.abs().max().item()), name
     assert int(res[1][1]["encoder.layer3.2.bn2.num_batches_tracked"]) == 1
     assert res[1][2] <= res[0][2] - 2 * 14                                 # >= 14 of the 16 bottlenecks chained: 2 fewer passes each
+
+
+@pytest.mark.parametrize("H,W", [(17, 19), (16, 12), (9, 9)])
+def test_max_pool_function(emulated, monkeypatch, H, W):
+    """fused.max_pool / _MaxPool3s2 (csrc/pool.cu routing) vs nn.MaxPool2d autograd, with ReLU-like inputs full of ties."""
+    monkeypatch.setitem(fused.ENABLED, "pool", True)
+    torch.manual_seed(H)
+    pool = nn.MaxPool2d(3, 2, 1, ceil_mode=True)
+    x32 = F.relu(torch.randn(2, 16, H, W)).bfloat16().float()                 # many exact zeros and bf16 ties
+    xa = _cl(x32.bfloat16()).requires_grad_(True)
+    y = fused.max_pool(xa, pool)
+    xb = x32.clone().requires_grad_(True)
+    yr = pool(xb)
+    assert y.shape == yr.shape and torch.equal(y.float(), yr)
+    g = torch.randn_like(yr).bfloat16().float()
+    y.backward(_cl(g.bfloat16()))
+    yr.backward(g)
+    assert (xa.grad.float() - xb.grad).abs().max() <= 2e-2 * xb.grad.abs().max()  # bf16 rounding of sums of <= 4 terms
+    with torch.no_grad():
+        assert torch.equal(fused.max_pool(xa.detach(), pool).float(), yr)      # no tap map without autograd
+    monkeypatch.setitem(fused.ENABLED, "pool", False)
+    assert torch.equal(fused.max_pool(xa.detach(), pool).float(), yr)

@@ -2,7 +2,7 @@
 // u2pl_conv_bf16_nhwc (plain / epilogue / statistics) and u2pl_conv_wgrad_bf16_nhwc against CPU loops.
 // Starts in about a second (no Python, no torch import), so it fits in the smallest GPU slot:
 //   nvcc -O2 -std=c++17 -o tools/cu/tc_selftest.bin tools/cu/tc_selftest.cu -ldl     (built here, runs on the box)
-//   ./tools/cu/tc_selftest.bin [conv|stats|xform|wgrad|all|perf]      (perf: CUDA-event timings at the network's layer shapes)
+//   ./tools/cu/tc_selftest.bin [conv|stats|xform|pool|wgrad|all|perf]      (perf: CUDA-event timings at the network's layer shapes)
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -20,6 +20,9 @@ typedef int (*conv_ex_fn)(const void *, const void *, void *, int64_t, int64_t, 
 typedef int64_t (*parts_fn)(int64_t, int64_t, int64_t, int);
 typedef int (*splits_fn)(int64_t, int64_t, int64_t, int64_t, int64_t);
 typedef int (*wgrad_fn)(const void *, const void *, float *, int64_t, int64_t, int64_t, int64_t, int64_t, int, void *);
+typedef int64_t (*pool_out_fn)(int64_t);
+typedef int (*pool_fn)(const void *, void *, void *, int64_t, int64_t, int64_t, int64_t, void *);
+typedef int (*pool_bwd_fn)(const void *, const void *, void *, int64_t, int64_t, int64_t, int64_t, void *);
 typedef const char *(*err_fn)(void);
 
 static uint16_t f2bf(float f)
@@ -47,7 +50,7 @@ template <typename T> static T *to_dev(const std::vector<T> &h)
     return d;
 }
 
-struct Lib { conv_fn conv; conv_ex_fn conv_ex; conv_stats_fn conv_stats; parts_fn parts; splits_fn splits; wgrad_fn wgrad; err_fn err; };
+struct Lib { conv_fn conv; conv_ex_fn conv_ex; conv_stats_fn conv_stats; parts_fn parts; splits_fn splits; wgrad_fn wgrad; err_fn err; pool_out_fn pool_out; pool_fn pool; pool_bwd_fn pool_bwd; };
 
 static int check_conv(const Lib &L, int N, int Cin, int H, int W, int Cout, int k, int d, bool epi, bool stats)
 {
@@ -237,6 +240,52 @@ static int check_wgrad(const Lib &L, int N, int Cin, int H, int W, int Cout, int
     return bad == 0 ? 0 : 1;
 }
 
+// 3x3 / stride 2 / pad 1 / ceil_mode max-pooling: forward values + taps, backward gather, against CPU loops (ATen's tie rule)
+static int check_pool(const Lib &L, int N, int H, int W, int C)
+{
+    const int Ho = static_cast<int>(L.pool_out(H)), Wo = static_cast<int>(L.pool_out(W));
+    const size_t nx = static_cast<size_t>(N) * H * W * C, ny = static_cast<size_t>(N) * Ho * Wo * C;
+    std::vector<uint16_t> x(nx), g(ny);
+    for (auto &v : x) { const float r = rnd(); v = f2bf(r > 0.0f ? roundf(r * 8.0f) / 8.0f : 0.0f); }    // ReLU-like: zeros and ties
+    for (auto &v : g) v = f2bf(rnd());
+    std::vector<float> yref(ny), dxref(nx, 0.0f);
+    std::vector<uint8_t> tref(ny);
+    for (int n = 0; n < N; ++n)
+        for (int ho = 0; ho < Ho; ++ho)
+            for (int wo = 0; wo < Wo; ++wo)
+                for (int c = 0; c < C; ++c) {
+                    float best = 0.0f;
+                    int tap = -1, bh = 0, bw = 0;
+                    for (int kh = 0; kh < 3; ++kh)
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const int h = 2 * ho - 1 + kh, w = 2 * wo - 1 + kw;
+                            if (h < 0 || h >= H || w < 0 || w >= W) continue;
+                            const float v = bf2f(x[((static_cast<size_t>(n) * H + h) * W + w) * C + c]);
+                            if (tap < 0 || v > best) { best = v; tap = kh * 3 + kw; bh = h; bw = w; }
+                        }
+                    const size_t o = ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * C + c;
+                    yref[o] = best; tref[o] = static_cast<uint8_t>(tap);
+                    dxref[((static_cast<size_t>(n) * H + bh) * W + bw) * C + c] += bf2f(g[o]);
+                }
+    uint16_t *dx_in = to_dev(x), *dg = to_dev(g), *dy = nullptr, *ddx = nullptr;
+    uint8_t *dtap = nullptr;
+    cudaMalloc(&dy, ny * 2); cudaMalloc(&ddx, nx * 2); cudaMalloc(&dtap, ny);
+    int rc = L.pool(dx_in, dy, dtap, N, H, W, C, nullptr);
+    if (rc == 0) rc = L.pool_bwd(dg, dtap, ddx, N, H, W, C, nullptr);
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (rc != 0 || e != cudaSuccess) { printf("pool: rc=%d cuda=%s err=%s\n", rc, cudaGetErrorString(e), L.err()); return 1; }
+    std::vector<uint16_t> y(ny), dxo(nx);
+    std::vector<uint8_t> tap(ny);
+    cudaMemcpy(y.data(), dy, ny * 2, cudaMemcpyDeviceToHost);
+    cudaMemcpy(tap.data(), dtap, ny, cudaMemcpyDeviceToHost);
+    cudaMemcpy(dxo.data(), ddx, nx * 2, cudaMemcpyDeviceToHost);
+    size_t bad = 0;
+    for (size_t i = 0; i < ny; ++i) if (bf2f(y[i]) != yref[i] || tap[i] != tref[i]) ++bad;
+    for (size_t i = 0; i < nx; ++i) if (!(fabsf(bf2f(dxo[i]) - dxref[i]) <= 2e-2f * fmaxf(1.0f, fabsf(dxref[i])))) ++bad;
+    printf("pool N=%d %dx%d -> %dx%d C=%d: mismatches=%zu  %s\n", N, H, W, Ho, Wo, C, bad, bad == 0 ? "OK" : "WRONG");
+    return bad == 0 ? 0 : 1;
+}
+
 // ---- timings at the network's layer shapes (T1 batch: 16 images), no CPU reference: TFLOP/s per kernel
 static uint16_t *dev_pattern(size_t n)
 {
@@ -251,6 +300,28 @@ static uint16_t *dev_pattern(size_t n)
 
 static void perf(const Lib &L)
 {
+    {   // stem max-pooling at the student batch: 32 x 257 x 257 x 128
+        const int N = 32, H = 257, W = 257, C = 128, Ho = static_cast<int>(L.pool_out(H)), Wo = static_cast<int>(L.pool_out(W));
+        const size_t nx = static_cast<size_t>(N) * H * W * C, ny = static_cast<size_t>(N) * Ho * Wo * C;
+        uint16_t *x = dev_pattern(nx), *y = dev_pattern(ny), *dx = nullptr;
+        uint8_t *tap = nullptr;
+        cudaMalloc(&dx, nx * 2); cudaMalloc(&tap, ny);
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        float ms[2];
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int i = 0; i < 13; ++i) {
+                if (i == 3) cudaEventRecord(a);
+                if (pass == 0) L.pool(x, y, tap, N, H, W, C, nullptr); else L.pool_bwd(y, tap, dx, N, H, W, C, nullptr);
+            }
+            cudaEventRecord(b); cudaEventSynchronize(b);
+            cudaEventElapsedTime(&ms[pass], a, b);
+            ms[pass] /= 10.0f;
+        }
+        printf("perf maxpool 32x257x257x128: fwd %.3f ms (%.0f GB/s), bwd %.3f ms (%.0f GB/s)\n", ms[0], (nx * 2 + ny * 3) / ms[0] / 1e6, ms[1],
+               (nx * 2 + ny * 3) / ms[1] / 1e6);
+        cudaFree(x); cudaFree(y); cudaFree(dx); cudaFree(tap);
+    }
     struct Shape { const char *name; int N, Cin, H, W, Cout, k, d; };
     const Shape shapes[] = {{"layer3.conv1 1x1 1024->256", 16, 1024, 65, 65, 256, 1, 1}, {"layer3.conv2 3x3 d2 256->256", 16, 256, 65, 65, 256, 3, 2},
                             {"layer3.conv3 1x1 256->1024", 16, 256, 65, 65, 1024, 1, 1}, {"layer4.conv2 3x3 d8 512->512", 16, 512, 65, 65, 512, 3, 8},
@@ -307,6 +378,10 @@ int main(int argc, char **argv)
     L.splits = reinterpret_cast<splits_fn>(dlsym(h, "u2pl_conv_wgrad_splits"));
     L.wgrad = reinterpret_cast<wgrad_fn>(dlsym(h, "u2pl_conv_wgrad_bf16_nhwc"));
     L.err = reinterpret_cast<err_fn>(dlsym(h, "u2pl_last_error"));
+    L.pool_out = reinterpret_cast<pool_out_fn>(dlsym(h, "u2pl_maxpool3s2_out"));
+    L.pool = reinterpret_cast<pool_fn>(dlsym(h, "u2pl_maxpool3s2_forward"));
+    L.pool_bwd = reinterpret_cast<pool_bwd_fn>(dlsym(h, "u2pl_maxpool3s2_backward"));
+    if (!L.pool_out || !L.pool || !L.pool_bwd) { fprintf(stderr, "missing pool symbol\n"); return 2; }
     if (!L.conv || !L.conv_ex || !L.conv_stats || !L.parts || !L.splits || !L.wgrad || !L.err) { fprintf(stderr, "missing symbol\n"); return 2; }
     int fails = 0;
     const bool all = !strcmp(what, "all");
@@ -324,6 +399,11 @@ int main(int argc, char **argv)
         fails += check_conv_xform(L, 2, 72, 11, 19, 40, 3, 2, false);        // Cin % 64 != 0, padding rows, 128-wide tile
         fails += check_conv_xform(L, 1, 128, 20, 35, 256, 3, 1, true);       // two channel blocks x nine taps, statistics
         fails += check_conv_xform(L, 3, 64, 5, 7, 136, 1, 1, false);         // flat 1x1, rows beyond the tensor
+    }
+    if (all || !strcmp(what, "pool")) {
+        fails += check_pool(L, 2, 17, 19, 16);
+        fails += check_pool(L, 1, 16, 12, 128);
+        fails += check_pool(L, 1, 257, 257, 8);
     }
     if (all || !strcmp(what, "wgrad")) {
         fails += check_wgrad(L, 1, 264, 7, 17, 136, 2);

@@ -28,6 +28,7 @@ if [ "${1:-1}" = "1" ]; then
   U2PL_INFONCE_DEPTH=4 timeout 200 python -m pytest tests/test_gpu_contra.py -q > $OUT/r2_pytest_contra_depth4.log 2>&1; echo "pytest contra depth4: $?"
   U2PL_TC_CONV=1 U2PL_TC_CHAIN=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_tcchain.json 2>$OUT/r2_bench_n1_tcchain.err; echo "bench ours+tc_conv+tc_chain: $?"
   U2PL_TC_CONV=1 U2PL_TC_TRAIN=1 U2PL_TC_CHAIN=1 U2PL_TC_WGRAD=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_tcall.json 2>$OUT/r2_bench_n1_tcall.err; echo "bench ours, every tensor-core path: $?"
+  U2PL_POOL=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_pool.json 2>$OUT/r2_bench_n1_pool.err; echo "bench ours+pool: $?"
   U2PL_WGRAD_STACK=1 timeout 200 python -m pytest tests/test_gpu_fused.py -q -k dilated > $OUT/r2_pytest_wgrad_stack.log 2>&1; echo "pytest wgrad_stack: $?"
   U2PL_WGRAD_STACK=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/r2_bench_n1_wgradstack.json 2>$OUT/r2_bench_n1_wgradstack.err; echo "bench ours+wgrad_stack: $?"
 else

@@ -56,6 +56,9 @@ SIGNATURES = {
                                        _P, _P, _P, c_int, _P, _P, _S]),
     "u2pl_conv_wgrad_splits": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int64]),
     "u2pl_conv_wgrad_bf16_nhwc": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, _S]),
+    "u2pl_maxpool3s2_out": (c_int64, [c_int64]),
+    "u2pl_maxpool3s2_forward": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, _S]),
+    "u2pl_maxpool3s2_backward": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, _S]),
     "u2pl_bn_parts": (c_int64, []),
     "u2pl_bn_stats": (c_int, [_P, c_int64, c_int64, _P, _P, _S]),
     "u2pl_bn_finalize": (c_int, [_P, c_int64, c_double, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _S]),

@@ -41,7 +41,9 @@ ENABLED = {"bn": True, "wgrad": True, "tc_conv": os.environ.get("U2PL_TC_CONV", 
            # no-grad TRAIN-mode chains (the teacher's second forward, train_semi.py:362-364): conv -> BN -> ReLU -> conv with
            # the inner BatchNorm + ReLU applied in the next convolution's operand load (conv_tc kXform), statistics from
            # the producing convolution's epilogue: the normalised activations between the convolutions never reach HBM
-           "tc_chain": os.environ.get("U2PL_TC_CHAIN", "0") == "1"}
+           "tc_chain": os.environ.get("U2PL_TC_CHAIN", "0") == "1",
+           # stem max-pooling through csrc/pool.cu instead of ATen's channels-last kernels (~0.6 TB/s)
+           "pool": os.environ.get("U2PL_POOL", "0") == "1"}
 
 
 def _world():
@@ -230,6 +232,40 @@ def conv_bn_act(x, conv, bn, relu=None, residual=None):
     _lib.check(lib.u2pl_bn_fold(C, _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), float(bn.eps),
                                 _p(scale), _p(shift), _stream()), "u2pl_bn_fold")
     return conv_bf16_nhwc(x, conv.weight, conv.dilation[0], scale, shift, residual, relu is not None and relu is not False)
+
+
+class _MaxPool3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        N, C, H, W = x.shape
+        Ho, Wo = int(lib.u2pl_maxpool3s2_out(H)), int(lib.u2pl_maxpool3s2_out(W))
+        y = torch.empty((N, C, Ho, Wo), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        need_bwd = any(ctx.needs_input_grad)
+        tap = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.device) if need_bwd else None
+        _lib.check(lib.u2pl_maxpool3s2_forward(_p(x), _p(y), _p(tap), N, H, W, C, _stream()), "u2pl_maxpool3s2_forward")
+        if need_bwd:
+            ctx.save_for_backward(tap)
+            ctx.shape = (N, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        tap, = ctx.saved_tensors
+        N, C, H, W = ctx.shape
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((N, C, H, W), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
+        _lib.check(lib.u2pl_maxpool3s2_backward(_p(dy), _p(tap), _p(dx), N, H, W, C, _stream()), "u2pl_maxpool3s2_backward")
+        return dx
+
+
+def max_pool(x, pool):
+    """The stem's nn.MaxPool2d(3, 2, 1, ceil_mode=True) on channels-last bf16 activations through csrc/pool.cu (opt-in)."""
+    ok = (ENABLED["pool"] and _is_cl_bf16(x) and x.shape[1] % 8 == 0 and isinstance(pool, nn.MaxPool2d)
+          and pool.kernel_size in (3, (3, 3)) and pool.stride in (2, (2, 2)) and pool.padding in (1, (1, 1))
+          and pool.dilation in (1, (1, 1)) and pool.ceil_mode and not pool.return_indices)
+    return _MaxPool3s2.apply(x) if ok else pool(x)
 
 
 def _finalize_train_bn(bn, sums, count):

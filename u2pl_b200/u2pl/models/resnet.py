@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from u2pl_b200.fused import (DilatedConv2d, StemConv2d, bn_act, chain_ok, conv_bn_act, conv_bn_relu_chain,
-                             run_sequential)
+                             max_pool, run_sequential)
 
 from .base import _norm
 
@@ -145,7 +145,7 @@ class ResNet(nn.Module):
         return nn.Sequential(*stack)
 
     def forward(self, x):
-        x = self.maxpool(bn_act(run_sequential(self.conv1, x), self.bn1, self.relu))
+        x = max_pool(bn_act(run_sequential(self.conv1, x), self.bn1, self.relu), self.maxpool)
         feats = []
         for idx in range(1, 5):
             x = getattr(self, f"layer{idx}")(x)
