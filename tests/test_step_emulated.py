@@ -103,3 +103,42 @@ def test_ohem_criterion_with_aux_on_emulated_abi(emulated, min_kept):
     t_kept = torch.where(torch.from_numpy(kept_main), target, torch.full_like(target, 255))
     torch.nn.functional.cross_entropy(mr, t_kept, ignore_index=255).backward()
     assert (main.grad - mr.grad).abs().max() <= 1e-6
+
+
+def test_sup_only_branch_on_emulated_abi(emulated):
+    """epoch < sup_only_epoch (train_semi.py:288-307): supervised CE on the labelled crops, teacher forward in train mode
+    for its BatchNorm statistics, zero unsupervised / contrastive losses, one SGD step, no EMA -- against plain torch."""
+    import u2pl_b200
+    u2pl_b200.install()
+    from u2pl.models.model_helper import ModelBuilder
+    from u2pl.utils.loss_helper import get_criterion
+    from u2pl.utils.lr_helper import get_optimizer
+    from u2pl_b200.step import SemiStep
+    C, crop = 21, 49
+    cfg = bench.make_cfg("tiny")
+    cfg["trainer"]["sup_only_epoch"] = 1
+    torch.manual_seed(11)
+    model = ModelBuilder(copy.deepcopy(cfg["net"]))
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.p = 0.0
+    teacher, ref_model = copy.deepcopy(model), copy.deepcopy(model)
+    t_before = copy.deepcopy(teacher.state_dict())
+    opt = get_optimizer([dict(params=model.parameters(), lr=0.01)], cfg["trainer"]["optimizer"])
+    ref_opt = torch.optim.SGD(ref_model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    step = SemiStep(model, teacher, opt, get_criterion(cfg), cfg, [[torch.zeros(0, 256)] for _ in range(C)],
+                    [torch.zeros(1, dtype=torch.long) for _ in range(C)], [30000] * C, amp=False, channels_last=False)
+    image_l, label_l, image_u = bench.synth_batch(7, 2, 2, crop, C)
+    losses = step(image_l, label_l, image_u, 0, 0, 100)
+    ref_model.train()
+    pred = torch.nn.functional.interpolate(ref_model(image_l)["pred"], label_l.shape[1:], mode="bilinear", align_corners=True)
+    ref_loss = torch.nn.functional.cross_entropy(pred, label_l, ignore_index=255)
+    ref_opt.zero_grad()
+    ref_loss.backward()
+    ref_opt.step()
+    assert abs(float(losses[0]) - float(ref_loss.detach())) <= 1e-5 and float(losses[1]) == 0.0 and float(losses[2]) == 0.0
+    for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
+        assert (a - b).abs().max() <= 1e-5, n
+    t_after = teacher.state_dict()
+    assert torch.equal(t_after["encoder.bn1.weight"], t_before["encoder.bn1.weight"])                 # no EMA in this branch
+    assert not torch.equal(t_after["encoder.bn1.running_mean"], t_before["encoder.bn1.running_mean"])  # but BN statistics moved
