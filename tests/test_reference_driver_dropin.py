@@ -15,6 +15,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DRIVER = "/root/reference/train_semi.py"
+DRIVER_SUP = "/root/reference/train_sup.py"
 
 CONFIG = """
 dataset:
@@ -85,8 +86,19 @@ else:                                                       # ---- the reference
     RB.get_loader = sb.get_loader                           # same synthetic crops in both runs
     _next = torch.utils.data.dataloader._BaseDataLoaderIter
     _next.next = _next.__next__
-calls = {{"unsup": [], "contra": []}}
+calls = {{"unsup": [], "contra": [], "sup": []}}
 import u2pl.utils.loss_helper as LH
+_gc = LH.get_criterion
+def _get_criterion(cfg):                                    # record what the supervised criterion returns (train_sup.py:218-220)
+    crit = _gc(cfg)
+    fwd = crit.forward
+    def rec(*a, **kw):
+        out = fwd(*a, **kw)
+        calls["sup"].append(float(out.detach()))
+        return out
+    crit.forward = rec
+    return crit
+LH.get_criterion = _get_criterion
 def _rec(f, k):
     def g(*a, **kw):
         out = f(*a, **kw)
@@ -95,37 +107,55 @@ def _rec(f, k):
     return g
 for name, key in (("compute_unsupervised_loss", "unsup"), ("compute_contra_memobank_loss", "contra")):
     setattr(LH, name, _rec(getattr(LH, name), key))
-sys.argv = ["train_semi.py", "--config", {config!r}, "--seed", "2", "--port", {port!r}]
+sys.argv = [os.path.basename({driver!r}), "--config", {config!r}, "--seed", "2", "--port", {port!r}]
 os.chdir(os.path.dirname({config!r}))
 runpy.run_path({driver!r}, run_name="__main__")
 import u2pl, json
 assert u2pl.__file__.startswith(u2pl_b200._HERE) == ({dropin!r} == "1"), u2pl.__file__
 ck = torch.load(os.path.join(os.path.dirname({config!r}), "checkpoints", "ckpt.pth"), map_location="cpu", weights_only=False)
-w = ck["teacher_state"]["module.decoder.classifier.8.weight"]
+w = ck["teacher_state" if "teacher_state" in ck else "model_state"]["module.decoder.classifier.8.weight"]
 print("DRIVER_DONE", json.dumps(dict(calls=calls, teacher_sum=float(w.double().abs().sum()), best=float(ck.get("best_miou", -1)))))
 """
 
 
-@pytest.mark.skipif(not os.path.exists(DRIVER), reason="the reference is only mounted in the build container")
-def test_unchanged_reference_driver_runs_on_the_dropin(tmp_path):
+def _run_both(tmp_path, driver, config_text):
     import json
     res = {}
     for dropin in ("0", "1"):                                              # control run on the reference's package, then the drop-in
         work = tmp_path / ("dropin" if dropin == "1" else "reference")
         work.mkdir()
         cfg = work / "config.yaml"
-        cfg.write_text(textwrap.dedent(CONFIG))
-        script = RUNNER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), config=str(cfg), driver=DRIVER, dropin=dropin,
+        cfg.write_text(textwrap.dedent(config_text))
+        script = RUNNER.format(root=ROOT, tests=os.path.join(ROOT, "tests"), config=str(cfg), driver=driver, dropin=dropin,
                                port=str(36000 + (os.getpid() + int(dropin)) % 2000))
         out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=900, cwd=str(work))
         tail = (out.stdout + out.stderr)[-3000:]
         assert out.returncode == 0 and "DRIVER_DONE" in out.stdout, tail
         res[dropin] = json.loads(out.stdout[out.stdout.index("DRIVER_DONE") + len("DRIVER_DONE"):].strip().splitlines()[0])
         assert (work / "checkpoints" / "ckpt.pth").exists()
-    a, b = res["0"], res["1"]
+    return res["0"], res["1"]
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="the reference is only mounted in the build container")
+def test_unchanged_reference_driver_runs_on_the_dropin(tmp_path):
+    a, b = _run_both(tmp_path, DRIVER, CONFIG)
     assert len(b["calls"]["unsup"]) == len(b["calls"]["contra"]) == 2      # the semi-supervised epoch ran both drop-in losses twice
     for k in ("unsup", "contra"):                                          # same driver, two packages: the same loss trajectory
         for x, y in zip(a["calls"][k], b["calls"][k]):
             assert abs(x - y) <= 1e-3 * max(1.0, abs(x)), (k, a["calls"], b["calls"])   # fp32 noise, amplified by one SGD step
     assert abs(a["teacher_sum"] - b["teacher_sum"]) <= 1e-4 * a["teacher_sum"]
     assert a["best"] == b["best"]
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER_SUP), reason="the reference is only mounted in the build container")
+def test_unchanged_train_sup_runs_on_the_dropin(tmp_path):
+    """BASELINE.json configs[0]: train_sup.py SupOnly, ResNet50-DeepLabv3+, two synthetic VOC crops, CPU -- the unchanged
+    driver on the reference's package (control) and on the drop-in: same supervised losses, weights and mIoU."""
+    cfg = CONFIG.replace("type: pascal_semi", "type: pascal").replace("n_sup: 4", "n_sup: 6") \
+        .replace("kwargs: {inner_planes: 256, dilations: [12, 24, 36]}",
+                 "kwargs: {inner_planes: 256, dilations: [12, 24, 36], rep_head: False}")      # as experiments/*/suponly/config.yaml
+    a, b = _run_both(tmp_path, DRIVER_SUP, cfg)
+    assert len(a["calls"]["sup"]) == len(b["calls"]["sup"]) == 6           # 3 iterations x 2 epochs
+    for x, y in zip(a["calls"]["sup"], b["calls"]["sup"]):
+        assert abs(x - y) <= 1e-3 * max(1.0, abs(x)), (a["calls"]["sup"], b["calls"]["sup"])
+    assert abs(a["teacher_sum"] - b["teacher_sum"]) <= 1e-4 * a["teacher_sum"] and a["best"] == b["best"]
