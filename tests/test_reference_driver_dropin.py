@@ -86,6 +86,13 @@ else:                                                       # ---- the reference
     RB.get_loader = sb.get_loader                           # same synthetic crops in both runs
     _next = torch.utils.data.dataloader._BaseDataLoaderIter
     _next.next = _next.__next__
+import u2pl.models.model_helper as MH                       # sharper initial predictions in BOTH runs, so that the contrastive
+_mb_init = MH.ModelBuilder.__init__                         # branch finds anchors (prob > 0.3) with an untrained network
+def _peaked(self, net_cfg):
+    _mb_init(self, net_cfg)
+    with torch.no_grad():
+        self.decoder.classifier[-1].weight.mul_(8.0)
+MH.ModelBuilder.__init__ = _peaked
 calls = {{"unsup": [], "contra": [], "sup": []}}
 import u2pl.utils.loss_helper as LH
 _gc = LH.get_criterion
@@ -143,6 +150,7 @@ def test_unchanged_reference_driver_runs_on_the_dropin(tmp_path):
     for k in ("unsup", "contra"):                                          # same driver, two packages: the same loss trajectory
         for x, y in zip(a["calls"][k], b["calls"][k]):
             assert abs(x - y) <= 1e-3 * max(1.0, abs(x)), (k, a["calls"], b["calls"])   # fp32 noise, amplified by one SGD step
+    assert max(a["calls"]["contra"]) > 0 and max(b["calls"]["contra"]) > 0   # the contrastive loss was really non-trivial
     assert abs(a["teacher_sum"] - b["teacher_sum"]) <= 1e-4 * a["teacher_sum"]
     assert a["best"] == b["best"]
 
