@@ -152,7 +152,7 @@ def test_unchanged_reference_driver_runs_on_the_dropin(tmp_path):
             assert abs(x - y) <= 1e-3 * max(1.0, abs(x)), (k, a["calls"], b["calls"])   # fp32 noise, amplified by one SGD step
     assert max(a["calls"]["contra"]) > 0 and max(b["calls"]["contra"]) > 0   # the contrastive loss was really non-trivial
     assert abs(a["teacher_sum"] - b["teacher_sum"]) <= 1e-4 * a["teacher_sum"]
-    assert a["best"] == b["best"]
+    assert abs(a["best"] - b["best"]) <= 2e-3                                  # mIoU: a few arg-max flips on near-tie pixels
 
 
 @pytest.mark.skipif(not os.path.exists(DRIVER_SUP), reason="the reference is only mounted in the build container")
@@ -166,4 +166,4 @@ def test_unchanged_train_sup_runs_on_the_dropin(tmp_path):
     assert len(a["calls"]["sup"]) == len(b["calls"]["sup"]) == 6           # 3 iterations x 2 epochs
     for x, y in zip(a["calls"]["sup"], b["calls"]["sup"]):
         assert abs(x - y) <= 1e-3 * max(1.0, abs(x)), (a["calls"]["sup"], b["calls"]["sup"])
-    assert abs(a["teacher_sum"] - b["teacher_sum"]) <= 1e-4 * a["teacher_sum"] and a["best"] == b["best"]
+    assert abs(a["teacher_sum"] - b["teacher_sum"]) <= 1e-4 * a["teacher_sum"] and abs(a["best"] - b["best"]) <= 2e-3
