@@ -280,3 +280,13 @@ def test_max_pool_function(emulated, monkeypatch, H, W):
         assert torch.equal(fused.max_pool(xa.detach(), pool).float(), yr)      # no tap map without autograd
     monkeypatch.setitem(fused.ENABLED, "pool", False)
     assert torch.equal(fused.max_pool(xa.detach(), pool).float(), yr)
+
+
+def test_smoke_tensor_core_helper_runs(emulated, monkeypatch, capsys):
+    """__graft_entry__._smoke_tensor_core: the informational tensor-core check smoke() appends on the GPU box, exercised
+    here on the CPU device over the emulated ABI (so that a typo cannot turn it into a false alarm there)."""
+    import __graft_entry__ as G
+    from u2pl_b200 import _lib
+    monkeypatch.setattr(_lib, "launch_count", lambda: 0)
+    assert G._smoke_tensor_core(torch, ops, _lib, device="cpu") is True
+    assert "smoke tensor-core ok" in capsys.readouterr().out
