@@ -18,6 +18,36 @@ def _up(t, size):
     return F.interpolate(t, size, mode="bilinear", align_corners=True)
 
 
+
+def _sup_criterion(cfg, pred, target, ignore=255):
+    """get_criterion's per-head loss (loss_helper.py:238-262): mean CE, or OhemCrossEntropy2dTensor.forward
+    (loss_helper.py:502-531: kept = mask_prob <= max(thresh, min_kept-th smallest mask_prob)) restated in torch."""
+    crit = cfg.get("criterion", {"type": "CELoss"})
+    if crit["type"] != "ohem":
+        return F.cross_entropy(pred, target, ignore_index=ignore)
+    thresh, min_kept = float(crit["kwargs"]["thresh"]), int(crit["kwargs"]["min_kept"])
+    b, c, h, w = pred.shape
+    t = target.reshape(-1)
+    valid = t.ne(ignore)                                                        # :505
+    t = t * valid.long()                                                        # :506
+    num_valid = int(valid.sum())
+    if not (min_kept > num_valid) and num_valid > 0:                            # :512-514
+        with torch.no_grad():
+            prob = F.softmax(pred, dim=1).transpose(0, 1).reshape(c, -1)        # :509-510
+            prob = prob.masked_fill(~valid, 1)                                  # :516
+            mask_prob = prob[t, torch.arange(t.numel(), device=t.device)]       # :517
+            threshold = thresh
+            if min_kept > 0:
+                _, index = mask_prob.sort()                                     # :520
+                kth = mask_prob[index[min(index.numel(), min_kept) - 1]]        # :521
+                if kth > thresh:                                                # :522-523
+                    threshold = kth
+                kept = mask_prob.le(threshold)                                  # :524
+                t = t * kept.long()
+                valid = valid & kept                                            # :526
+    t = t.masked_fill(~valid, ignore).view(b, h, w)                             # :528-529
+    return F.cross_entropy(pred, t, ignore_index=ignore)
+
 class ReferenceStep:
     def __init__(self, student_state, teacher_state, cfg, arch="resnet101", lr=0.001, momentum=0.9,
                  weight_decay=1e-4, head_lr_mult=10, bank_dim=256):
@@ -61,10 +91,9 @@ class ReferenceStep:
         pred_all, rep_all = outs["pred"], outs["rep"]
         pred_l_large, pred_u_large = _up(pred_all[:nl], (h, w)), _up(pred_all[nl:], (h, w))
         # supervised loss (:352-358)
-        sup = F.cross_entropy(pred_l_large, label_l, ignore_index=255)
+        sup = _sup_criterion(cfg, pred_l_large, label_l)
         if self.aux:
-            sup = sup + cfg["net"]["aux_loss"]["loss_weight"] * F.cross_entropy(_up(outs["aux"][:nl], (h, w)), label_l,
-                                                                                ignore_index=255)
+            sup = sup + cfg["net"]["aux_loss"]["loss_weight"] * _sup_criterion(cfg, _up(outs["aux"][:nl], (h, w)), label_l)
         # T2 (:360-374)
         T.training = True
         with torch.no_grad():

@@ -46,7 +46,7 @@ def test_conv_bn_act_falls_back_off_gpu():
     with torch.no_grad():
         got = fused.conv_bn_act(x, conv, bn, relu, r)
         assert torch.allclose(got, relu(bn(conv(x)) + r), atol=1e-6)
-    assert fused.ENABLED["tc_conv"] is False                      # opt-in only (U2PL_TC_CONV=1)
+    assert fused.ENABLED["tc_conv"] in ("auto", "1", False)       # per-layer policy by default (U2PL_TC_CONV=auto)
 
 
 @pytest.mark.parametrize("k,d", [(1, 1), (3, 1), (3, 2), (3, 5)])

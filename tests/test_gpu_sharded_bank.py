@@ -3,8 +3,7 @@ give bit-identical losses, gradients and bank contents to the replicated device 
 single-GPU tests pin to the oracle.  Each rank feeds its own slice of the golden fixture's steps, so keys from both
 ranks interleave in rank order exactly as in utils.py:21-38.
 
-OPT-IN (U2PL_BANK_SHARDED_TEST=1 and >= 2 visible GPUs): written after round 1's GPU minutes were spent; first run:
-    gpurun --gpus 2 -- 'U2PL_BANK_SHARDED_TEST=1 python -m pytest tests/test_gpu_sharded_bank.py -x -q'"""
+Runs whenever >= 2 GPUs are visible:  gpurun --gpus 2 -- 'python -m pytest tests/test_gpu_sharded_bank.py -x -q'"""
 import os
 
 import numpy as np
@@ -12,8 +11,7 @@ import pytest
 import torch
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("U2PL_BANK_SHARDED_TEST", "0") != "1" or torch.cuda.device_count() < 2,
-                                 reason="needs U2PL_BANK_SHARDED_TEST=1 and two GPUs")]
+              pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")]
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "contra_c21.npz")
 

@@ -81,12 +81,16 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     from . import build as _build
-    if build_if_missing:
-        try:
-            _build.build()                     # no-op when the source digest matches the stamp; rebuilds a stale library
-        except RuntimeError:
-            if not os.path.exists(LIB_PATH):
-                raise
+    if build_if_missing and not _build.is_current():
+        # stale or missing library: rebuild (under build.py's file lock, atomically replaced).  A failed rebuild is
+        # fatal -- loading a stale library against new Python signatures is worse than stopping.  The only tolerated
+        # case is a machine without nvcc whose library travelled with its stamp removed (then the ABI version and the
+        # symbol table below are the check).
+        import shutil
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            _build.build()
+        elif not os.path.exists(LIB_PATH):
+            raise U2PLNativeError(f"{LIB_PATH} is missing and nvcc is not available (there is no fallback path)")
     if not os.path.exists(LIB_PATH):
         raise U2PLNativeError(f"{LIB_PATH} is missing; run `python -m u2pl_b200.build` (there is no fallback path)")
     lib = ctypes.CDLL(LIB_PATH)

@@ -26,24 +26,46 @@ from .ops import _p, _stream
 
 import os
 
-# "tc_conv": eval-mode conv + BN (+residual, +ReLU) through the tcgen05 implicit-GEMM kernel (csrc/conv_tc.cu).
-# Off unless U2PL_TC_CONV=1: written after round 1's GPU minutes were spent; correct on a B200 in the torch-free self-test
-# (profiles/r01_tc_selftest.txt), but untimed, and this Python routing has not executed on a GPU yet.
-# "wgrad_stack": stride-1 dilated weight gradient as ONE GEMM against nine shifted, zero-padded copies of the (small)
-# output gradient instead of nine GEMMs over cropped copies of the (large) input.  Same status: opt-in, unmeasured.
-# "tc_train": train-mode forward AND data gradient of every eligible stride-1 convolution through the same kernel
-# (the data gradient of a stride-1 "same" convolution is a convolution of the output gradient with the flipped,
-# transposed weight); weight gradients stay with cuDNN / the GEMM paths above.  Same status.
-ENABLED = {"bn": True, "wgrad": True, "tc_conv": os.environ.get("U2PL_TC_CONV", "0") == "1",
-           "wgrad_stack": os.environ.get("U2PL_WGRAD_STACK", "0") == "1",
-           "tc_train": os.environ.get("U2PL_TC_TRAIN", "0") == "1",
-           "tc_wgrad": os.environ.get("U2PL_TC_WGRAD", "0") == "1",   # 3x3 stride-1 weight gradients via csrc/wgrad_tc.cu
-           # no-grad TRAIN-mode chains (the teacher's second forward, train_semi.py:362-364): conv -> BN -> ReLU -> conv with
-           # the inner BatchNorm + ReLU applied in the next convolution's operand load (conv_tc kXform), statistics from
-           # the producing convolution's epilogue: the normalised activations between the convolutions never reach HBM
-           "tc_chain": os.environ.get("U2PL_TC_CHAIN", "0") == "1",
-           # stem max-pooling through csrc/pool.cu instead of ATen's channels-last kernels (~0.6 TB/s)
-           "pool": os.environ.get("U2PL_POOL", "0") == "1"}
+def _env(name, default):
+    return os.environ.get(name, default) == "1"
+
+
+# Routing switches (env var = override for A/B runs; defaults are what B200 measurements picked, profiles/r02_*):
+# "tc_conv"    eval-mode, no-grad conv + BN (+residual, +ReLU) as ONE tcgen05 implicit-GEMM kernel (csrc/conv_tc.cu).
+#              "auto" (default) = per layer, where the fused kernel beats cuDNN conv + a separate bn_apply pass on B200
+#              (every 1x1 convolution and the dilation >= 18 3x3s, `_tc_conv_wins`); "1" = every eligible layer; "0" = off.
+# "tc_dilated" forward of 3x3 stride-1 convolutions with dilation >= 18 (ASPP d=24/36) through the tcgen05 kernel in
+#              every mode: cuDNN 9 picks an sm80 kernel there (1.28 ms vs 0.52 ms per 16 images at 2048 -> 256).
+# "wgrad_stack" stride-1 dilated weight gradient as ONE GEMM against nine shifted copies of the (small) output gradient
+#              instead of nine GEMMs over cropped copies of the (large) input: -13 ms per V16 step.
+# "tc_train"   train-mode forward AND data gradient of every eligible stride-1 convolution through conv_tc (statistics in
+#              the epilogue); opt-in: the 1-CTA kernel runs at 0.65 of cuDNN's 2-CTA kernels, the step gets slower.
+# "tc_wgrad"   3x3 stride-1 weight gradients via csrc/wgrad_tc.cu (MN-major operands in place).
+# "tc_chain"   no-grad TRAIN-mode chains (teacher's second forward, train_semi.py:362-364): inner BatchNorm + ReLU applied
+#              in the next convolution's operand load (conv_tc kXform), statistics from the producing conv's epilogue.
+# "pool"       stem max-pooling through csrc/pool.cu instead of ATen's channels-last kernels (~0.6 TB/s).
+ENABLED = {"bn": True, "wgrad": True,
+           "tc_conv": os.environ.get("U2PL_TC_CONV", "auto"),
+           "tc_dilated": _env("U2PL_TC_DILATED", "1"),
+           "wgrad_stack": _env("U2PL_WGRAD_STACK", "1"),
+           "tc_train": _env("U2PL_TC_TRAIN", "0"),
+           "tc_wgrad": _env("U2PL_TC_WGRAD", "0"),
+           "tc_chain": _env("U2PL_TC_CHAIN", "0"),
+           "pool": _env("U2PL_POOL", "1")}
+if ENABLED["tc_conv"] not in ("auto", "1"):
+    ENABLED["tc_conv"] = False
+TC_DILATION_MIN = 18            # 3x3 convolutions at or above this dilation always run on conv_tc (see "tc_dilated")
+FALLBACKS = {"bn_module": 0}    # calls that left the fused kernels for an nn.Module (reported by bench.py)
+
+
+def _tc_conv_wins(conv, residual):
+    """B200 measurements (profiles/r02_conv_bench.jsonl, 16 x 65x65 / 129x129): fused conv+BN(+res)+ReLU vs cuDNN conv +
+    bn_apply.  1x1: the epilogue fusion always wins (44 vs 35+30 us at 1024->256; 88 vs 44+150 us at 256->1024 with
+    the residual).  3x3: the 1-CTA kernel reaches 1.0-1.2 PF/s against cuDNN's 1.5-1.6 PF/s 2-CTA kernels, so only the
+    large dilations (where cuDNN falls back to an sm80 kernel) win."""
+    if ENABLED["tc_conv"] in ("1", True):
+        return True
+    return conv.kernel_size == (1, 1) or conv.dilation[0] >= TC_DILATION_MIN
 
 
 def _world():
@@ -138,6 +160,8 @@ def bn_act(x, bn, relu=None, residual=None, sums=None):
         sync = isinstance(bn, nn.SyncBatchNorm) and bn.training and _world() > 1
         return _BNAct.apply(x, bn.weight, bn.bias, residual, bn, relu is not None and relu is not False, sync,
                             sums if bn.training else None)
+    if x.is_cuda:
+        FALLBACKS["bn_module"] += 1                 # fp32 runs, Cout not a multiple of 8 (classifier), 1x1 pooled maps
     y = bn(x)
     if residual is not None:
         y = y + residual
@@ -205,7 +229,7 @@ def _geometry_only(conv):
 def _tc_conv_ok(x, conv, bn, residual):
     k, d = conv.kernel_size[0], conv.dilation[0]
     return (ENABLED["tc_conv"] and not bn.training and not torch.is_grad_enabled() and _is_cl_bf16(x)
-            and isinstance(conv, nn.Conv2d) and isinstance(bn, (nn.BatchNorm2d, nn.SyncBatchNorm))
+            and isinstance(conv, nn.Conv2d) and _tc_conv_wins(conv, residual) and isinstance(bn, (nn.BatchNorm2d, nn.SyncBatchNorm))
             and conv.kernel_size in ((1, 1), (3, 3)) and conv.stride == (1, 1) and conv.dilation == (d, d)
             and conv.padding == (d * (k // 2), d * (k // 2)) and conv.groups == 1 and conv.bias is None
             and conv.padding_mode == "zeros" and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0
@@ -355,7 +379,7 @@ class _DilatedConvFn(torch.autograd.Function):
     def forward(ctx, x, w, dilation, stride):
         ctx.save_for_backward(x, w)
         ctx.cfg = (dilation, stride)
-        if ENABLED["tc_train"] and stride == 1 and _is_cl_bf16(x):
+        if stride == 1 and _is_cl_bf16(x) and (ENABLED["tc_train"] or (ENABLED["tc_dilated"] and dilation >= TC_DILATION_MIN)):
             from .ops import conv_bf16_nhwc
             return conv_bf16_nhwc(x, w, dilation)
         return F.conv2d(x, w, None, stride, dilation, dilation)
@@ -425,10 +449,15 @@ class DilatedConv2d(nn.Conv2d):
 
     def forward(self, x):
         d, s = self.dilation[0], self.stride[0]
-        fast = (ENABLED["wgrad"] and x.is_cuda and self.kernel_size == (3, 3) and self.stride == (s, s)
-                and self.padding == (d, d) and self.dilation == (d, d) and self.groups == 1
-                and self.bias is None and torch.is_autocast_enabled() and torch.is_grad_enabled())
+        geom = (x.is_cuda and self.kernel_size == (3, 3) and self.stride == (s, s) and self.padding == (d, d)
+                and self.dilation == (d, d) and self.groups == 1 and self.bias is None and torch.is_autocast_enabled())
+        fast = ENABLED["wgrad"] and geom and torch.is_grad_enabled()
         if not fast:
+            if (geom and ENABLED["tc_dilated"] and s == 1 and d >= TC_DILATION_MIN and self.in_channels % 8 == 0
+                    and self.out_channels % 8 == 0):          # no-grad passes (teacher): same kernel, no autograd node
+                from .ops import conv_bf16_nhwc
+                xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                return conv_bf16_nhwc(xb, self.weight, d)
             return super().forward(x)
         xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         wb = self.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
