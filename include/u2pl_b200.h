@@ -84,6 +84,26 @@ int u2pl_partition_target(const float *entropy, int64_t *target, int64_t n, int6
                           uint8_t *drop_mask, int64_t *n_kept, void *stream);
 
 /* ------------------------------------------------------------------------
+ * A6/A7  the whole chain in ONE launch: entropy + percentile thresholds + partition
+ * replaces: loss_helper.py:35-44 (and train_semi.py:402-415 for the extra percentiles) in a single persistent
+ * cooperative kernel (one CTA per SM, the CTA's slice of entropy keys stays in shared memory between the
+ * passes; csrc/entropy_partition.cu `entropy_chain_kernel`).  Same results, bit for bit, as
+ * u2pl_entropy_thresholds_fast followed by u2pl_partition_target on a copy of target_in:
+ *   entropy [B,HW], thresh [nq], n_valid as above;
+ *   target_out[i] = (entropy[i] >= thresh[part_idx] && target_in[i] != ignore) ? ignore : target_in[i]
+ *   (target_in is NOT modified -- the caller's clone of loss_helper.py:381 is the output buffer),
+ *   drop_mask (uint8, may be NULL), n_kept = #(target_out != ignore).
+ * Falls back internally to the multi-launch kernels when B*HW exceeds what the CTAs' shared memory holds
+ * (> 36864 pixels per SM) or C is not 19 / 21.  Workspace: u2pl_entropy_fast_ws_bytes.
+ * ---------------------------------------------------------------------- */
+int u2pl_entropy_partition_fused(const float *logits, const int64_t *target_in,
+                                 int64_t B, int64_t C, int64_t HW, int64_t ignore,
+                                 const float *h_percents, int nq, int part_idx,
+                                 float *entropy, float *thresh, int64_t *n_valid,
+                                 int64_t *target_out, uint8_t *drop_mask, int64_t *n_kept,
+                                 void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
  * A8  low / high entropy masks (train_semi.py:408-418), evaluated at arbitrary
  * pixel positions so the nearest-neighbour down-sample of :427-453 can be fused:
  *   out_low[j]  = (entropy[idx[j]] <= thresh[lo_idx]) & (target[idx[j]] != ignore)

@@ -309,6 +309,12 @@ class FakeLoss:
 
     u2pl_entropy_thresholds_fast = u2pl_entropy_thresholds
 
+    def u2pl_entropy_partition_fused(self, logits, target_in, B, C, HW, ignore, hq, nq, part_idx, ent, thresh, n_valid,
+                                     target_out, mask, n_kept, ws, ws_bytes, stream):
+        self.u2pl_entropy_thresholds(logits, target_in, B, C, HW, ignore, hq, nq, ent, thresh, n_valid, ws, ws_bytes, stream)
+        _arr(target_out, B * HW, ctypes.c_int64)[:] = _arr(target_in, B * HW, ctypes.c_int64)
+        return self.u2pl_partition_target(ent, target_out, B * HW, ignore, thresh, part_idx, mask, n_kept, stream)
+
     def u2pl_partition_target(self, entropy, target, n, ignore, thresh, idx, mask, n_kept, stream):
         e = _arr(entropy, n, ctypes.c_float)
         t = _arr(target, n, ctypes.c_int64)

@@ -91,6 +91,58 @@ def test_entropy_thresholds_bit_exact(B, C, H, W, ign, percents, exact_map):
         assert th[j] == np.percentile(ent_or[valid], q)                     # numpy itself agrees
 
 
+def _fused_vs_two_step(ops, x, target, percents, part_idx):
+    """u2pl_entropy_partition_fused (one cooperative launch) must equal thresholds_fast + partition_target, bit for bit."""
+    ent, thresh, n_valid = ops.entropy_thresholds(x, target, percents)
+    t2 = target.clone()
+    n_kept, mask = ops.partition_target_(ent, t2, thresh, part_idx, want_mask=True)
+    t_in = target.clone()
+    ent_f, thresh_f, n_valid_f, t_f, n_kept_f, mask_f = ops.entropy_partition(x, t_in, percents, part_idx, want_mask=True)
+    assert torch.equal(t_in, target)                                            # input untouched
+    assert torch.equal(thresh.view(torch.int32), thresh_f.view(torch.int32))    # NaN-safe bit comparison
+    assert n_valid.item() == n_valid_f.item() and n_kept.item() == n_kept_f.item()
+    assert torch.equal(t2, t_f) and torch.equal(mask, mask_f)
+    assert torch.equal(ent.view(torch.int32), ent_f.view(torch.int32))
+    return ent_f, thresh_f, t_f, n_kept_f
+
+
+@pytest.mark.parametrize("B,C,H,W,ign,percents,part", [
+    (2, 21, 33, 37, 0.0, [90.0], 0),
+    (3, 19, 29, 31, 0.3, [80.0, 12.5, 87.5], 0),
+    (1, 21, 5, 3, 0.0, [20.0, 80.0], 1),                  # tiny, ragged: one CTA, slice of 16 pixels
+    (2, 21, 64, 64, 0.95, [95.0], 0),                     # almost everything ignored
+    (4, 21, 129, 131, 0.1, [90.0, 10.0, 90.0, 100.0], 2), # four percentiles, several CTAs, repeated percentile
+    (1, 7, 40, 41, 0.1, [50.0], 0),                       # class count without a specialisation: multi-launch path inside
+])
+def test_fused_chain_equals_two_step(B, C, H, W, ign, percents, part):
+    ops = _ops()
+    rng = np.random.default_rng(B * 1000 + C * 10 + H)
+    x, target = _rand_case(rng, B, C, H, W, ign)
+    ent, thresh, t_f, n_kept = _fused_vs_two_step(ops, _dev(x), _dev(target), percents, part)
+    ent_or = port.entropy(x)                                                    # and against the oracle
+    valid = target != 255
+    th = thresh.cpu().numpy()
+    for j, q in enumerate(percents):
+        assert th[j].view(np.uint32) == np.float32(port.percentile(ent_or[valid], q)).view(np.uint32)
+    want = target.copy()
+    want[(ent_or >= th[part]) & valid] = 255
+    assert np.array_equal(t_f.cpu().numpy(), want)                              # bit-exact reliable / unreliable index set
+    assert n_kept.item() == int((want != 255).sum())
+
+
+def test_fused_chain_edge_cases():
+    ops = _ops()
+    rng = np.random.default_rng(3)
+    x, target = _rand_case(rng, 1, 21, 16, 16)
+    target[:] = 255                                                             # empty population -> NaN thresholds, nothing dropped
+    _, thresh, t_f, n_kept = _fused_vs_two_step(ops, _dev(x), _dev(target), [80.0], 0)
+    assert np.isnan(thresh.cpu().numpy()[0]) and n_kept.item() == 0 and bool((t_f == 255).all())
+    x = np.zeros((2, 21, 24, 24), np.float32)                                   # every pixel ties: everything is a candidate
+    x[1, 3] = 5.0
+    target = np.zeros((2, 24, 24), np.int64)
+    _fused_vs_two_step(ops, _dev(x), _dev(target), [50.0, 99.0], 0)
+
+
 def test_all_ignored_gives_nan():
     ops = _ops()
     rng = np.random.default_rng(0)
@@ -182,6 +234,9 @@ def test_full_size_v16_properties():
     xs = x.permute(0, 2, 3, 1).reshape(-1, C)[torch.from_numpy(idx).cuda()].cpu().numpy()      # [50000, C]
     ent_s = port.entropy(np.ascontiguousarray(xs.T[None]))[0]                                  # B=1, HW=50000
     assert np.array_equal(ent_s.view(np.uint32), e[idx].view(np.uint32))
+    # the single cooperative launch at the benchmark size: bit-identical to the multi-launch chain
+    _fused_vs_two_step(ops, x, target, percents, 0)
+    _fused_vs_two_step(ops, x, target, [90.0, 10.0, 90.0], 0)                          # the step's own three percentiles
 
 
 @pytest.mark.parametrize("name", ["ohem_c19", "ohem_c19_kth"])

@@ -389,11 +389,19 @@ int main(int argc, char **argv)
         fails += check_conv(L, 1, 64, 13, 11, 136, 1, 1, false, false);      // flat 1x1, 256-wide channel tile, partial tiles
         fails += check_conv(L, 1, 72, 20, 24, 40, 3, 3, true, false);        // Cin % 64 != 0, epilogue, 128-wide tile
         fails += check_conv(L, 2, 128, 17, 33, 256, 3, 2, true, false);      // two K blocks per tap, 256-wide tile
+        // CTA-pair kernel (conv_tc2.cu, Cout > 128): several channel tiles with a partial last one + residual through TMA,
+        // odd number of pixel tiles (the peer's last tile is beyond the tensor), flat 1x1 with an even tile count
+        fails += check_conv(L, 2, 128, 17, 33, 520, 3, 2, true, false);
+        fails += check_conv(L, 1, 64, 23, 17, 256, 3, 5, true, false);
+        fails += check_conv(L, 1, 256, 30, 40, 512, 1, 1, true, false);
+        fails += check_conv(L, 3, 192, 9, 40, 264, 3, 1, false, false);
     }
     if (all || !strcmp(what, "stats")) {
         fails += check_conv(L, 2, 64, 17, 19, 128, 3, 1, false, true);
         fails += check_conv(L, 1, 128, 20, 35, 256, 3, 2, false, true);      // 256-wide tile (largest shared-memory footprint)
         fails += check_conv(L, 3, 64, 5, 7, 264, 1, 1, false, true);         // flat 1x1, partial channel tile
+        fails += check_conv(L, 3, 64, 23, 17, 264, 3, 2, false, true);       // pair kernel: odd tile count, partial channel tile
+        fails += check_conv(L, 2, 64, 16, 32, 512, 1, 1, false, true);       // pair kernel: flat, even tile count, two channel tiles
     }
     if (all || !strcmp(what, "xform")) {
         fails += check_conv_xform(L, 2, 72, 11, 19, 40, 3, 2, false);        // Cin % 64 != 0, padding rows, 128-wide tile

@@ -7,7 +7,7 @@ import bench
 
 def main():
     args = types.SimpleNamespace(gpus=1, steps=1, warmup=2, impl="ours", workload=os.environ.get("WL", "v16"),
-                                 fp32=False, no_cpu_baseline=True)
+                                 fp32=False, no_cpu_baseline=True, no_eager_baseline=True, phases=False)
     os.environ["U2PL_BENCH_FAST"] = "1"
     from torch.profiler import profile, ProfilerActivity
     # warm-up outside the profiler

@@ -23,6 +23,8 @@ SIGNATURES = {
     "u2pl_entropy_fast_ws_bytes": (c_size_t, [c_int64, c_int64]),
     "u2pl_entropy_thresholds_fast": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, POINTER(c_float), c_int,
                                              _P, _P, _P, _P, c_size_t, _S]),
+    "u2pl_entropy_partition_fused": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, POINTER(c_float), c_int, c_int,
+                                             _P, _P, _P, _P, _P, _P, _P, c_size_t, _S]),
     "u2pl_partition_target": (c_int, [_P, _P, c_int64, c_int64, _P, c_int, _P, _P, _S]),
     "u2pl_entropy_masks": (c_int, [_P, _P, _P, c_int64, c_int64, _P, c_int, c_int, _P, _P, _S]),
     "u2pl_ce_ws_bytes": (c_size_t, [c_int64, c_int64]),

@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "conv_tc2.cuh"
 
 namespace u2pl {
 
@@ -372,6 +373,8 @@ static int conv_launch(const void *x, const void *wgt, void *out, int64_t n, int
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(out) |
          reinterpret_cast<uintptr_t>(residual)) & 15)
         return bad_arg("conv_bf16_nhwc: operands must be 16-byte aligned");
+    if (conv_tc2_eligible(cout, in_scale != nullptr || in_shift != nullptr || in_relu != 0))      // CTA-pair kernel (conv_tc2.cu)
+        return conv_tc2_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, scale, shift, residual, relu, stat_part, what, stream);
     ConvParams p;
     CUtensorMap mx, mw;
     bool ok;
@@ -443,10 +446,18 @@ extern "C" int u2pl_conv_bf16_nhwc(const void *x, const void *wgt, void *out, in
                        "conv_bf16_nhwc", stream);
 }
 
-extern "C" int64_t u2pl_conv_stat_parts(int64_t n, int64_t h, int64_t w, int ksize)
+static int64_t stat_parts_1cta(int64_t n, int64_t h, int64_t w, int ksize)
 {
     if (ksize == 1) return (n * h * w + convtc::kBM - 1) / convtc::kBM;
     return n * ((h + 7) / 8) * ((w + 15) / 16);
+}
+
+// rows of the caller's partial-sum buffer: the larger of the two kernels' needs (the pair kernel writes two per pixel tile)
+extern "C" int64_t u2pl_conv_stat_parts(int64_t n, int64_t h, int64_t w, int ksize) { return conv_tc2_stat_parts(n, h, w, ksize); }
+
+static int stat_parts_used(int64_t n, int64_t h, int64_t w, int64_t cout, int ksize, bool xform)
+{
+    return static_cast<int>(conv_tc2_eligible(cout, xform) ? conv_tc2_stat_parts(n, h, w, ksize) : stat_parts_1cta(n, h, w, ksize));
 }
 
 extern "C" int u2pl_conv_bf16_nhwc_stats(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w,
@@ -457,7 +468,7 @@ extern "C" int u2pl_conv_bf16_nhwc_stats(const void *x, const void *wgt, void *o
     int rc = conv_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, stat_part,
                          "conv_bf16_nhwc_stats", stream);
     if (rc != 0) return rc;
-    return bn_reduce_parts(stat_part, static_cast<int>(u2pl_conv_stat_parts(n, h, w, ksize)), static_cast<int>(2 * cout), sums, stream);
+    return bn_reduce_parts(stat_part, stat_parts_used(n, h, w, cout, ksize, false), static_cast<int>(2 * cout), sums, stream);
 }
 
 extern "C" int u2pl_conv_bf16_nhwc_ex(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w, int64_t cin,
@@ -469,5 +480,6 @@ extern "C" int u2pl_conv_bf16_nhwc_ex(const void *x, const void *wgt, void *out,
     int rc = conv_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, in_scale, in_shift, in_relu, scale, shift, residual, relu,
                          stat_part, "conv_bf16_nhwc_ex", stream);
     if (rc != 0 || !stat_part) return rc;
-    return bn_reduce_parts(stat_part, static_cast<int>(u2pl_conv_stat_parts(n, h, w, ksize)), static_cast<int>(2 * cout), sums, stream);
+    return bn_reduce_parts(stat_part, stat_parts_used(n, h, w, cout, ksize, in_scale != nullptr || in_shift != nullptr || in_relu != 0),
+                           static_cast<int>(2 * cout), sums, stream);
 }

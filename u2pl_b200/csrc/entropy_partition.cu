@@ -14,6 +14,7 @@
 // HBM-bound by design: K1 moves (4C + 8 + 4 + 4) B/pixel, K7 moves 4+8+8+1 B/pixel,
 // K3/K5 re-read 4 B/pixel of keys out of the 126 MB L2.  Nothing synchronises the host.
 #include <algorithm>
+#include <cstdlib>
 #include "arith.cuh"
 #include "common.cuh"
 
@@ -36,6 +37,7 @@ struct SelState {
     uint32_t below[kMaxT];          //                 valid pixels surely below the candidate band
     float    val[kMaxT];            //                 exact order statistics
     uint32_t band[kMaxT];           //                 candidate band (list / counter index) of every target
+    uint32_t bar;                   // fused chain: grid-barrier arrival counter (zeroed with the rest of the state)
 };
 
 struct Percents { float q[kMaxQ]; int use_rank; uint32_t rank; };   // use_rank: one explicit order statistic instead
@@ -745,6 +747,357 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
     if (tid < U && s_below[tid]) atomicAdd(&st->below[tid], s_below[tid]);
 }
 
+
+// ====================================================================== the whole chain as ONE cooperative kernel
+// entropy -> percentile thresholds -> reliable/unreliable partition in a single persistent launch (one 1024-thread CTA
+// per SM, cudaLaunchCooperativeKernel so that the software grid barrier below cannot deadlock).  CTA b owns the
+// contiguous pixel slice [b*slice, (b+1)*slice) and keeps that slice's order-preserving entropy keys in SHARED MEMORY
+// (<= 144 KB) from the first pass to the last, so the logits are streamed from HBM exactly once and every later pass
+// (10-bit refinement histogram, candidate band test, partition compare) reads shared memory instead of re-scanning
+// 16.8 MB of keys out of L2 from four separate launches:
+//   P1  fast entropy of the slice (coalesced, C loads in flight per thread) -> ent[], s_keys[], 12-bit histogram
+//   P2  select1 on the merged histogram (every CTA, redundantly) + 10-bit histogram of the slice's keys inside the
+//       target bins
+//   P3  22-bit bin per target rank -> candidate bands; band test on s_keys; candidates are re-evaluated under the
+//       arithmetic contract (exact value back into ent[] and s_keys[], exact key appended to the band's global list)
+//   P4  CTA t < T: exact radix select of target t inside its candidate list
+//   P5  numpy lerp -> thresholds (every CTA, redundantly; CTA 0 publishes) and the partition of the slice:
+//       target_out = (entropy >= thresh[part_idx] && valid) ? ignore : target_in, drop mask, kept count
+// Four grid barriers (~2 us each) replace four launches + four L2 scans.  Soundness argument: see the two-level path.
+constexpr int kChainThreads = 1024;
+constexpr int kChainMaxSlice = 36864;                     // keys per CTA: 144 KB of the 227 KB
+
+__device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t goal)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        uint32_t v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < goal);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// block-wide exclusive scan position of `cnt` (one value per thread, 1024 threads); returns excl, total in *tot
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t cnt, uint32_t *warp_tot)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    __syncthreads();                                       // warp_tot free (previous use read)
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < wid; ++w) base += warp_tot[w];
+    return base + inc - cnt;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kChainThreads, 1)
+entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict__ target_in, uint32_t HW, uint32_t N,
+                     uint32_t slice, int64_t ignore, Percents pc, int nq, int part_idx,
+                     float *__restrict__ ent, float *__restrict__ thresh, int64_t *__restrict__ n_valid,
+                     int64_t *__restrict__ target_out, uint8_t *__restrict__ drop_mask, unsigned long long *__restrict__ n_kept,
+                     uint32_t *__restrict__ hist1, uint32_t *__restrict__ hist2, SelState *__restrict__ st,
+                     uint32_t *__restrict__ lists)
+{
+    extern __shared__ uint32_t chain_smem[];
+    uint32_t *s_keys = chain_smem;                         // [slice]
+    uint32_t *s_h1 = s_keys + ((slice + 3u) & ~3u);        // [4096]: 12-bit histogram; later candidate staging / select histogram
+    uint32_t *s_h2 = s_h1 + kBins1;                        // [kMaxT][1024]: 10-bit histograms; later candidate band masks
+    __shared__ uint32_t warp_tot[32], s_prefix[kMaxT], s_rank[kMaxT], s_grank[kMaxT], s_pre22[kMaxT], s_band[kMaxT], s_below[kMaxT];
+    __shared__ float s_gamma[kMaxQ], s_lo[kMaxT], s_hi[kMaxT], s_thr[kMaxQ];
+    __shared__ uint32_t s_n, s_cnt, s_sel_prefix, s_sel_rank;
+    __shared__ int s_nband;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int T = 2 * nq;
+    const uint32_t G = gridDim.x;
+    const uint32_t base = blockIdx.x * slice;
+    const uint32_t cnt = (base < N) ? min(slice, N - base) : 0u;
+
+    // ---------------------------------------------------------------- P1
+    for (int j = tid; j < kBins1; j += kChainThreads) s_h1[j] = 0;
+    __syncthreads();
+    for (uint32_t j = tid; j < cnt; j += kChainThreads) {
+        const uint32_t i = base + j;
+        const uint32_t b = i / HW, p = i - b * HW;
+        const float *x = logits + static_cast<size_t>(b) * C * HW + p;
+        float v[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
+        const int64_t t = __ldg(target_in + i);
+        const float h = entropy_fast_of<C>(v);
+        ent[i] = h;
+        const bool valid = (t != ignore);
+        const uint32_t key = valid ? float_key(h) : kInvalidKey;
+        s_keys[j] = key;
+        if (valid) hist_add(s_h1, key >> 20);
+    }
+    __syncthreads();
+    for (int j = tid; j < kBins1; j += kChainThreads)
+        if (s_h1[j]) atomicAdd(&hist1[j], s_h1[j]);
+    grid_barrier(&st->bar, G);
+
+    // ---------------------------------------------------------------- P2: select1 (thread t owns bins 4t..4t+3)
+    {
+        const uint4 q = __ldcg(reinterpret_cast<const uint4 *>(hist1) + tid);
+        const uint32_t loc[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t sum = loc[0] + loc[1] + loc[2] + loc[3];
+        const uint32_t excl = block_excl_scan_1024(sum, warp_tot);
+        if (tid == kChainThreads - 1) s_n = excl + sum;
+        __syncthreads();
+        const uint32_t n = s_n;
+        if (tid == 0) {
+            const float nm1 = __uint2float_rn(n ? n - 1u : 0u);
+            for (int j = 0; j < nq; ++j) {                 // numpy 2.x float32 virtual index (see select1_kernel)
+                const float q32 = __fdiv_rn(pc.q[j], 100.0f);
+                const float v = __fmul_rn(nm1, q32);
+                const float fl = floorf(v);
+                uint32_t lo, hi;
+                if (n == 0) { lo = hi = 0; }
+                else if (v >= nm1) { lo = hi = n - 1u; }
+                else { lo = static_cast<uint32_t>(fl); hi = lo + 1u; }
+                s_gamma[j] = __fadd_rn(v, -fl);
+                s_grank[2 * j] = lo;
+                s_grank[2 * j + 1] = hi;
+            }
+        }
+        __syncthreads();
+        if (n != 0) {
+            for (int t = 0; t < T; ++t) {
+                const uint32_t r = s_grank[t];
+                if (r >= excl && r < excl + sum) {
+                    uint32_t cum = excl;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (r < cum + loc[j]) { s_prefix[t] = tid * 4 + j; s_rank[t] = r - cum; break; }
+                        cum += loc[j];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t n_all = s_n;                            // uniform across the grid (same histogram everywhere)
+    if (n_all != 0) {
+        for (int j = tid; j < T * kBinsR; j += kChainThreads) s_h2[j] = 0;
+        uint32_t pre[kMaxT];                               // targets with equal prefixes share the first one's histogram
+#pragma unroll
+        for (int t = 0; t < kMaxT; ++t) {
+            pre[t] = (t < T) ? s_prefix[t] : kInvalidKey;
+#pragma unroll
+            for (int u = 0; u < t; ++u)
+                if (t < T && s_prefix[u] == s_prefix[t]) pre[t] = kInvalidKey;
+        }
+        __syncthreads();
+        for (uint32_t j = tid; j < cnt; j += kChainThreads) {
+            const uint32_t key = s_keys[j];
+            if (key == kInvalidKey) continue;
+            const uint32_t hi = key >> 20;
+            uint32_t mt = 0;
+#pragma unroll
+            for (int t = 0; t < kMaxT; ++t) mt |= (hi == pre[t]) ? (1u << t) : 0u;
+            if (mt) {
+                const uint32_t bin = (key >> 10) & (kBinsR - 1);
+                const uint32_t peers = __match_any_sync(__activemask(), (mt << 10) | bin);
+                if (lane == __ffs(peers) - 1) {
+                    const uint32_t c2 = __popc(peers);
+                    while (mt) { const int t = __ffs(mt) - 1; mt &= mt - 1; atomicAdd(&s_h2[t * kBinsR + bin], c2); }
+                }
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < T * kBinsR; j += kChainThreads)
+            if (s_h2[j]) atomicAdd(&hist2[j], s_h2[j]);
+    }
+    grid_barrier(&st->bar, 2 * G);
+
+    // ---------------------------------------------------------------- P3: 22-bit bins, bands, candidates
+    if (n_all != 0) {
+        for (int t = 0; t < T; ++t) {                      // thread j owns sub-bin j of target t's histogram
+            int owner = t;
+            for (int u = t - 1; u >= 0; --u) if (s_prefix[u] == s_prefix[t]) owner = u;
+            const uint32_t c2 = __ldcg(hist2 + owner * kBinsR + tid);
+            const uint32_t excl = block_excl_scan_1024(c2, warp_tot);
+            const uint32_t r = s_rank[t];
+            if (r >= excl && r < excl + c2) s_pre22[t] = (s_prefix[t] << 10) | static_cast<uint32_t>(tid);
+        }
+        __syncthreads();
+        if (tid == 0) {                                    // merge targets with the same bin into one candidate band
+            int nb = 0;
+            for (int t = 0; t < T; ++t) {
+                int b = -1;
+                for (int u = 0; u < t; ++u) if (s_pre22[u] == s_pre22[t]) { b = static_cast<int>(s_band[u]); break; }
+                if (b < 0) {
+                    b = nb++;
+                    const uint32_t p22 = s_pre22[t];
+                    s_lo[b] = key_float(p22 << 10) - 3.0f * kDelta;
+                    s_hi[b] = (p22 == 0x3FFFFFu) ? __uint_as_float(0x7f800000u) : key_float((p22 + 1u) << 10) + 3.0f * kDelta;
+                }
+                s_band[t] = static_cast<uint32_t>(b);
+                if (blockIdx.x == 0) st->band[t] = static_cast<uint32_t>(b);
+            }
+            s_nband = nb;
+            if (blockIdx.x == 0) {
+                st->n = n_all;
+                for (int t = 0; t < T; ++t) st->grank[t] = s_grank[t];
+                for (int j = 0; j < nq; ++j) st->gamma[j] = s_gamma[j];
+            }
+        }
+        if (tid < kMaxT) s_below[tid] = 0;
+        __syncthreads();
+        const int U = s_nband;
+        float lo[kMaxT], hi[kMaxT];
+        uint32_t below[kMaxT];
+#pragma unroll
+        for (int u = 0; u < kMaxT; ++u) {
+            below[u] = 0;
+            lo[u] = (u < U) ? s_lo[u] : __uint_as_float(0xff800000u);     // -inf: never below, never inside
+            hi[u] = (u < U) ? s_hi[u] : lo[u];
+        }
+        uint32_t *s_pix = s_h1;                            // candidates of the current tile: slice-local index ...
+        uint8_t *s_hit = reinterpret_cast<uint8_t *>(s_h2); // ... and the bands it falls into
+        for (uint32_t tb = 0; tb < cnt; tb += kBins1) {
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < kBins1 / kChainThreads; ++it) {
+                const uint32_t j = tb + it * kChainThreads + tid;
+                const uint32_t k = (j < cnt) ? s_keys[j] : kInvalidKey;
+                if (k == kInvalidKey) continue;
+                const float h = key_float(k);
+                uint32_t hit = 0;
+#pragma unroll
+                for (int u = 0; u < kMaxT; ++u) {
+                    below[u] += (h < lo[u]) ? 1u : 0u;
+                    hit |= (h >= lo[u] && h < hi[u]) ? (1u << u) : 0u;
+                }
+                if (hit) {
+                    const uint32_t pos = atomicAdd(&s_cnt, 1u);
+                    s_pix[pos] = j;
+                    s_hit[pos] = static_cast<uint8_t>(hit);
+                }
+            }
+            __syncthreads();
+            const uint32_t nc = s_cnt;
+            for (uint32_t c2 = tid; c2 < nc; c2 += kChainThreads) {       // exact (contract) entropy of the candidates
+                const uint32_t j = s_pix[c2];
+                uint32_t hit = s_hit[c2];
+                const uint32_t i = base + j;
+                const uint32_t b = i / HW, p = i - b * HW;
+                const float *x = logits + static_cast<size_t>(b) * C * HW + p;
+                float v[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
+                const float e = entropy_of<C>(v);
+                ent[i] = e;
+                const uint32_t ek = float_key(e);
+                s_keys[j] = ek;
+                while (hit) {
+                    const int u = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    const uint32_t pos = atomicAdd(&st->cnt[u], 1u);
+                    lists[static_cast<size_t>(u) * N + pos] = ek;
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int u = 0; u < kMaxT; ++u) {
+            const uint32_t sm = static_cast<uint32_t>(warp_sum_i(static_cast<int>(below[u])));
+            if (lane == 0 && sm) atomicAdd(&s_below[u], sm);
+        }
+        __syncthreads();
+        if (tid < U && s_below[tid]) atomicAdd(&st->below[tid], s_below[tid]);
+    }
+    grid_barrier(&st->bar, 3 * G);
+
+    // ---------------------------------------------------------------- P4: exact select, CTA t < T
+    if (n_all != 0 && static_cast<int>(blockIdx.x) < T) {
+        const int t = blockIdx.x;
+        uint32_t *hist = s_h1;                             // [2048]
+        const uint32_t u = s_band[t];
+        const uint32_t n = __ldcg(&st->cnt[u]);
+        const uint32_t r0 = s_grank[t] - __ldcg(&st->below[u]);           // unsigned: a violated invariant shows as r0 >= n
+        const uint32_t *list = lists + static_cast<size_t>(u) * N;
+        if (r0 >= n) {
+            if (tid == 0) st->val[t] = __uint_as_float(0x7fc00000u);
+        } else {
+            if (tid == 0) { s_sel_prefix = 0; s_sel_rank = r0; }
+            const int shifts[3] = {21, 10, 0}, nbits[3] = {11, 11, 10};
+            for (int pass = 0; pass < 3; ++pass) {
+                hist[tid] = 0; hist[tid + 1024] = 0;
+                __syncthreads();
+                const uint32_t pre = s_sel_prefix, r = s_sel_rank;
+                const int sh = shifts[pass], hb = sh + nbits[pass];
+                const uint32_t mask = (1u << nbits[pass]) - 1u;
+                for (uint32_t j = tid; j < n; j += kChainThreads) {
+                    const uint32_t k = __ldcg(list + j);
+                    if (pass == 0 || (k >> hb) == pre) atomicAdd(&hist[(k >> sh) & mask], 1u);
+                }
+                __syncthreads();
+                const uint32_t c0 = hist[2 * tid], c1 = hist[2 * tid + 1], sum = c0 + c1;
+                const uint32_t excl = block_excl_scan_1024(sum, warp_tot);
+                __syncthreads();
+                if (r >= excl && r < excl + sum) {
+                    const uint32_t bin = (r < excl + c0) ? 2 * tid : 2 * tid + 1;
+                    s_sel_prefix = (pre << nbits[pass]) | bin;
+                    s_sel_rank = r - ((r < excl + c0) ? excl : excl + c0);
+                }
+                __syncthreads();
+            }
+            if (tid == 0) st->val[t] = key_float(s_sel_prefix);
+        }
+    }
+    grid_barrier(&st->bar, 4 * G);
+
+    // ---------------------------------------------------------------- P5: thresholds + partition of the slice
+    if (tid == 0) {
+        for (int j = 0; j < nq; ++j) {
+            float r = __uint_as_float(0x7fc00000u);
+            if (n_all != 0) {                              // numpy _lerp (see select_refine_kernel)
+                const float a = __ldcg(&st->val[2 * j]), b = __ldcg(&st->val[2 * j + 1]), g = s_gamma[j];
+                const float d = __fadd_rn(b, -a);
+                r = __fadd_rn(a, __fmul_rn(d, g));
+                if (g >= 0.5f) r = __fadd_rn(b, -__fmul_rn(d, __fadd_rn(1.0f, -g)));
+            }
+            s_thr[j] = r;
+            if (blockIdx.x == 0) thresh[j] = r;
+        }
+        if (blockIdx.x == 0 && n_valid) *n_valid = static_cast<int64_t>(n_all);
+    }
+    __syncthreads();
+    if (target_out != nullptr) {
+        const float th = s_thr[part_idx];
+        int kept = 0;
+        for (uint32_t j = tid; j < cnt; j += kChainThreads) {
+            const uint32_t i = base + j;
+            const int64_t t = __ldg(target_in + i);
+            const uint32_t key = s_keys[j];
+            const bool valid = (key != kInvalidKey);
+            const bool drop = valid && (key_float(key) >= th);
+            target_out[i] = drop ? ignore : t;
+            if (drop_mask) drop_mask[i] = drop ? 1 : 0;
+            kept += (valid && !drop) ? 1 : 0;
+        }
+        kept = warp_sum_i(kept);
+        __syncthreads();
+        if (lane == 0) warp_tot[wid] = static_cast<uint32_t>(kept);
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long s2 = 0;
+            for (int w = 0; w < kChainThreads / 32; ++w) s2 += warp_tot[w];
+            if (s2) atomicAdd(n_kept, s2);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ OHEM (loss_helper.py:502-531)
 // mask_prob = softmax(pred)[target] (1.0 where target == ignore), computed under the arithmetic
 // contract because the kept set is cut by an order statistic of it (:520-524).
@@ -1005,6 +1358,87 @@ extern "C" int u2pl_partition_target(const float *entropy, int64_t *target, int6
     partition_kernel<<<grid, 256, 0, s>>>(entropy, target, static_cast<uint32_t>(n), ignore, thresh, thresh_idx,
                                           drop_mask, reinterpret_cast<unsigned long long *>(n_kept));
     return check_launch("partition");
+}
+
+// One cooperative launch for the whole chain (entropy_chain_kernel); falls back to the multi-launch two-level path +
+// partition_kernel when the pixel slice of a CTA would not fit in shared memory or the class count is not specialised.
+template <int C>
+static int launch_chain(const float *logits, const int64_t *target_in, uint32_t hw, uint32_t N, int64_t ignore, const Percents &pc,
+                        int nq, int part_idx, float *entropy, float *thresh, int64_t *n_valid, int64_t *target_out,
+                        uint8_t *drop_mask, int64_t *n_kept, const EntropyWs &w, uint32_t *lists, cudaStream_t s, bool *launched)
+{
+    *launched = false;
+    int dev = 0, sms = kNumSMs, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop) return 0;
+    uint32_t grid = static_cast<uint32_t>(std::min<long long>(sms, std::max<long long>(1, (static_cast<long long>(N) + 4095) / 4096)));
+    uint32_t slice = (N + grid - 1) / grid;
+    slice = (slice + 3u) & ~3u;
+    if (slice > static_cast<uint32_t>(kChainMaxSlice)) return 0;
+    const size_t smem = (static_cast<size_t>(slice) + kBins1 + kMaxT * kBinsR) * 4;
+    static bool configured = false;
+    if (!configured) {
+        const size_t max_smem = (static_cast<size_t>(kChainMaxSlice) + kBins1 + kMaxT * kBinsR) * 4;
+        cudaError_t e = cudaFuncSetAttribute(entropy_chain_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem));
+        if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+        configured = true;
+    }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_chain_kernel<C>, kChainThreads, smem);
+    if (per_sm < 1 || static_cast<long long>(per_sm) * sms < grid) return 0;
+    Percents pcc = pc;
+    unsigned long long *nk = reinterpret_cast<unsigned long long *>(n_kept);
+    uint32_t hw_ = hw, N_ = N;
+    void *args[] = {&logits, &target_in, &hw_, &N_, &slice, &ignore, &pcc, &nq, &part_idx, &entropy, &thresh, &n_valid,
+                    &target_out, &drop_mask, &nk, const_cast<uint32_t **>(&w.hist1), const_cast<uint32_t **>(&w.hist2),
+                    const_cast<SelState **>(&w.st), &lists};
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(entropy_chain_kernel<C>), dim3(grid), dim3(kChainThreads),
+                                                args, smem, s);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
+    *launched = true;
+    return check_launch("entropy_chain");
+}
+
+extern "C" int u2pl_entropy_partition_fused(const float *logits, const int64_t *target_in,
+                                            int64_t B, int64_t C, int64_t HW, int64_t ignore,
+                                            const float *h_percents, int nq, int part_idx,
+                                            float *entropy, float *thresh, int64_t *n_valid,
+                                            int64_t *target_out, uint8_t *drop_mask, int64_t *n_kept,
+                                            void *ws, size_t ws_bytes, void *stream)
+{
+    if (B <= 0 || C <= 0 || HW <= 0) return bad_arg("entropy_partition_fused: empty shape");
+    if (nq < 1 || nq > kMaxQ || part_idx < 0 || part_idx >= nq) return bad_arg("entropy_partition_fused: bad nq / part_idx");
+    if (B * HW >= (1LL << 31)) return bad_arg("entropy_partition_fused: B*HW must be < 2^31");
+    if (!target_out || !n_kept) return bad_arg("entropy_partition_fused: target_out and n_kept are required");
+    if (ws_bytes < fast_ws_layout(B * HW, nullptr, nullptr, nullptr)) { set_error("entropy_partition_fused: workspace too small"); return U2PL_E_WS_SMALL; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t N = static_cast<uint32_t>(B * HW), hw = static_cast<uint32_t>(HW);
+    static const bool disabled = [] { const char *e = getenv("U2PL_ENTROPY_CHAIN"); return e && e[0] == '0'; }();
+    if ((C == 19 || C == 21) && !disabled) {
+        EntropyWs w;
+        uint32_t *lists = nullptr;
+        fast_ws_layout(B * HW, ws, &w, &lists);
+        cudaError_t e = cudaMemsetAsync(w.hist1, 0, w.zero_bytes, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(n_kept, 0, sizeof(int64_t), s);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
+        Percents pc;
+        pc.use_rank = 0; pc.rank = 0;
+        for (int j = 0; j < kMaxQ; ++j) pc.q[j] = (j < nq) ? h_percents[j] : 0.0f;
+        bool launched = false;
+        int rc = (C == 19) ? launch_chain<19>(logits, target_in, hw, N, ignore, pc, nq, part_idx, entropy, thresh, n_valid, target_out,
+                                              drop_mask, n_kept, w, lists, s, &launched)
+                           : launch_chain<21>(logits, target_in, hw, N, ignore, pc, nq, part_idx, entropy, thresh, n_valid, target_out,
+                                              drop_mask, n_kept, w, lists, s, &launched);
+        if (rc != 0 || launched) return rc;
+    }
+    // multi-launch path: thresholds, then copy + partition
+    int rc = u2pl_entropy_thresholds_fast(logits, target_in, B, C, HW, ignore, h_percents, nq, entropy, thresh, n_valid, ws, ws_bytes, stream);
+    if (rc != 0) return rc;
+    cudaError_t e = cudaMemcpyAsync(target_out, target_in, static_cast<size_t>(N) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
+    return u2pl_partition_target(entropy, target_out, static_cast<int64_t>(N), ignore, thresh, part_idx, drop_mask, n_kept, stream);
 }
 
 extern "C" int u2pl_entropy_masks(const float *entropy, const int64_t *target, const int64_t *idx,

@@ -40,7 +40,8 @@ def _env(name, default):
 #              instead of nine GEMMs over cropped copies of the (large) input: -13 ms per V16 step.
 # "tc_train"   train-mode forward AND data gradient of every eligible stride-1 convolution through conv_tc (statistics in
 #              the epilogue); opt-in: the 1-CTA kernel runs at 0.65 of cuDNN's 2-CTA kernels, the step gets slower.
-# "tc_wgrad"   3x3 stride-1 weight gradients via csrc/wgrad_tc.cu (MN-major operands in place).
+# "tc_wgrad"   3x3 stride-1 weight gradients of the DilatedConv2d layers via csrc/wgrad_tc.cu (MN-major operands read in
+#              place, 0.74-1.16 PFLOP/s): -4.8 ms of backward per V16 step against the stacked-GEMM form.
 # "tc_chain"   no-grad TRAIN-mode chains (teacher's second forward, train_semi.py:362-364): inner BatchNorm + ReLU applied
 #              in the next convolution's operand load (conv_tc kXform), statistics from the producing conv's epilogue.
 # "pool"       stem max-pooling through csrc/pool.cu instead of ATen's channels-last kernels (~0.6 TB/s).
@@ -49,10 +50,10 @@ ENABLED = {"bn": True, "wgrad": True,
            "tc_dilated": _env("U2PL_TC_DILATED", "1"),
            "wgrad_stack": _env("U2PL_WGRAD_STACK", "1"),
            "tc_train": _env("U2PL_TC_TRAIN", "0"),
-           "tc_wgrad": _env("U2PL_TC_WGRAD", "0"),
+           "tc_wgrad": _env("U2PL_TC_WGRAD", "1"),
            "tc_chain": _env("U2PL_TC_CHAIN", "0"),
            "pool": _env("U2PL_POOL", "1")}
-if ENABLED["tc_conv"] not in ("auto", "1"):
+if ENABLED["tc_conv"] not in ("auto", "1", "1x1"):
     ENABLED["tc_conv"] = False
 TC_DILATION_MIN = 18            # 3x3 convolutions at or above this dilation always run on conv_tc (see "tc_dilated")
 FALLBACKS = {"bn_module": 0}    # calls that left the fused kernels for an nn.Module (reported by bench.py)
@@ -65,7 +66,11 @@ def _tc_conv_wins(conv, residual):
     large dilations (where cuDNN falls back to an sm80 kernel) win."""
     if ENABLED["tc_conv"] in ("1", True):
         return True
-    return conv.kernel_size == (1, 1) or conv.dilation[0] >= TC_DILATION_MIN
+    if ENABLED["tc_conv"] == "1x1":                            # A/B switch: every 1x1 as well
+        return conv.kernel_size == (1, 1) or conv.dilation[0] >= TC_DILATION_MIN
+    # measured in the step (gpurun_out/r2b_*): routing every 1x1 of T1 through the 1-CTA kernel made T1 slower (22.1 vs
+    # 18.2 ms) -- its per-thread 16-byte epilogue stores lose on the memory-bound 1x1 layers; only the large dilations win
+    return conv.kernel_size == (3, 3) and conv.dilation[0] >= TC_DILATION_MIN
 
 
 def _world():

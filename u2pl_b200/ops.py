@@ -75,6 +75,34 @@ def entropy_thresholds(logits, target, percents, ignore=255, exact_map=False):
     return ent, thresh, n_valid
 
 
+def entropy_partition(logits, target, percents, part_idx=0, ignore=255, want_mask=False):
+    """loss_helper.py:35-44 (+ the extra percentiles of train_semi.py:402-415) in ONE kernel launch
+    (u2pl_entropy_partition_fused): returns (entropy [B,H,W], thresh [len(percents)], n_valid, new_target, n_kept, drop_mask).
+    `target` is left untouched; `new_target` is the clone-with-unreliable-pixels-ignored the reference builds in place."""
+    _need_cuda(logits, target)
+    lib = _lib.load()
+    logits = _f32c(logits)
+    target = target.contiguous()
+    assert target.dtype == torch.int64
+    B, C, H, W = logits.shape
+    HW = H * W
+    nq = len(percents)
+    dev = logits.device
+    ent = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    thresh = torch.empty(nq, dtype=torch.float32, device=dev)
+    n_valid = torch.empty((), dtype=torch.int64, device=dev)
+    n_kept = torch.empty((), dtype=torch.int64, device=dev)
+    new_target = torch.empty_like(target)
+    mask = torch.empty(target.shape, dtype=torch.uint8, device=dev) if want_mask else None
+    hq = (ctypes.c_float * nq)(*[float(q) for q in percents])
+    ws = _workspace("entropy_fast", lib.u2pl_entropy_fast_ws_bytes(B, HW), dev)
+    rc = lib.u2pl_entropy_partition_fused(_p(logits), _p(target), B, C, HW, int(ignore), hq, nq, int(part_idx),
+                                          _p(ent), _p(thresh), _p(n_valid), _p(new_target), _p(mask), _p(n_kept),
+                                          _p(ws), ws.numel(), _stream())
+    _lib.check(rc, "u2pl_entropy_partition_fused")
+    return ent, thresh, n_valid, new_target, n_kept, mask
+
+
 def partition_target_(entropy, target, thresh, thresh_idx=0, ignore=255, want_mask=False):
     """In place: target[(entropy >= thresh[idx]) & (target != ignore)] = ignore  (loss_helper.py:41-43).
     Returns (n_kept int64 device scalar, drop mask uint8 or None)."""
@@ -193,8 +221,9 @@ def unsup_loss_from_entropy(predict, target, ent, thresh, thresh_idx=0, ignore=2
 
 def unsup_loss(predict, target, percent, pred_teacher, ignore=255):
     """compute_unsupervised_loss(predict, target, percent, pred_teacher) -- loss_helper.py:30-48."""
-    ent, thresh, _ = entropy_thresholds(pred_teacher.detach(), target, [float(percent)], ignore)
-    return unsup_loss_from_entropy(predict, target, ent, thresh, 0, ignore)
+    _, _, _, new_target, n_kept, _ = entropy_partition(pred_teacher.detach(), target, [float(percent)], 0, ignore)
+    target.copy_(new_target)                                  # the reference mutates the caller's tensor (loss_helper.py:43)
+    return _UnsupCE.apply(predict, target, n_kept, ignore)
 
 
 # --------------------------------------------------------------------------- A8 helpers

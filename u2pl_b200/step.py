@@ -141,10 +141,8 @@ class SemiStep:
                 alpha_t = cfg_contra["low_entropy_threshold"] * (1 - epoch / trainer["epochs"])
                 percents += [alpha_t, 100 - alpha_t]
             label_u_aug = label_u_aug.contiguous()
-            target = label_u_aug.clone()
-            ev = self._event()
-            ent, thresh, _ = ops.entropy_thresholds(pred_u_large_teacher, label_u_aug, percents)
-            n_kept, _ = ops.partition_target_(ent, target, thresh, 0)          # loss_helper.py:41-43
+            ev = self._event()                                                 # one launch: loss_helper.py:35-44 + :402-415
+            ent, thresh, _, target, n_kept, _ = ops.entropy_partition(pred_u_large_teacher, label_u_aug, percents, 0)
             self._event(ev, "entropy_partition")
             unsup_loss = ops.unsup_ce(pred_u_large, target, n_kept) * trainer["unsupervised"].get("loss_weight", 1)
             if cfg_contra:
