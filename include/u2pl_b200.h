@@ -115,6 +115,26 @@ int u2pl_entropy_masks(const float *entropy, const int64_t *target, const int64_
                        float *out_low, float *out_high, void *stream);
 
 /* ------------------------------------------------------------------------
+ * A3 / N2  consumers of the x4 bilinear up-sampling (align_corners=True) fused with it (csrc/upsample_ce.cu): the
+ * full-resolution [B,C,H,W] logits of train_semi.py:317-324,344-358 are never materialised.
+ * low [B,C,h,w] fp32 NCHW contiguous; target [B,H,W] int64; C in {19, 21} (u2pl_upsample_fused_supported).
+ *   u2pl_up_softmax_max   replaces F.interpolate -> F.softmax(dim=1) -> torch.max(dim=1)   (train_semi.py:318-324)
+ *   u2pl_upce_forward     replaces F.interpolate -> F.cross_entropy(ignore_index): nll_sum over valid pixels + their count
+ *                         (train_semi.py:344-358 with loss_helper.py:313-319 / :44-46)
+ *   u2pl_upce_backward    grad_low [B,C,h,w] = interpolation^T((softmax - onehot) * scale[0]) -- the CE backward and
+ *                         upsample_bilinear2d_backward in one gather pass (no atomics, deterministic)
+ * ---------------------------------------------------------------------- */
+int u2pl_upsample_fused_supported(int64_t C);
+size_t u2pl_upce_ws_bytes(void);
+int u2pl_up_softmax_max(const float *low, int64_t B, int64_t C, int64_t h, int64_t w, int64_t H, int64_t W,
+                        float *out_prob, int64_t *out_label, void *stream);
+int u2pl_upce_forward(const float *low, const int64_t *target, int64_t B, int64_t C, int64_t h, int64_t w,
+                      int64_t H, int64_t W, int64_t ignore, float *nll_sum, int64_t *n_used,
+                      void *ws, size_t ws_bytes, void *stream);
+int u2pl_upce_backward(const float *low, const int64_t *target, int64_t B, int64_t C, int64_t h, int64_t w,
+                       int64_t H, int64_t W, int64_t ignore, const float *scale, float *grad_low, void *stream);
+
+/* ------------------------------------------------------------------------
  * A6/A12  cross entropy with ignore_index, forward and backward
  * replaces: F.cross_entropy(predict, target, ignore_index=255) at
  *           loss_helper.py:46 and nn.CrossEntropyLoss at :265,313-319.

@@ -326,6 +326,42 @@ class FakeLoss:
         _arr(n_kept, 1, ctypes.c_int64)[0] = int((t != ignore).sum())
         return 0
 
+    def u2pl_upsample_fused_supported(self, C):
+        return 1 if C in (19, 21) else 0
+
+    def u2pl_upce_ws_bytes(self):
+        return 148 * 8 * 8
+
+    @staticmethod
+    def _up(low, B, C, h, w, H, W):
+        x = torch.from_numpy(_arr(low, B * C * h * w, ctypes.c_float).reshape(B, C, h, w).copy())
+        return F.interpolate(x, (H, W), mode="bilinear", align_corners=True)
+
+    def u2pl_up_softmax_max(self, low, B, C, h, w, H, W, out_prob, out_label, stream):
+        prob, lab = torch.max(F.softmax(self._up(low, B, C, h, w, H, W), dim=1), dim=1)
+        _arr(out_prob, B * H * W, ctypes.c_float).reshape(B, H, W)[:] = prob.numpy()
+        _arr(out_label, B * H * W, ctypes.c_int64).reshape(B, H, W)[:] = lab.numpy()
+        return 0
+
+    def u2pl_upce_forward(self, low, target, B, C, h, w, H, W, ignore, nll, n_used, ws, ws_bytes, stream):
+        x = self._up(low, B, C, h, w, H, W).numpy().reshape(B, C, H * W)
+        t = _arr(target, B * H * W, ctypes.c_int64).reshape(B, H * W)
+        s, n = port.cross_entropy_sum(x, t, ignore)
+        _arr(nll, 1, ctypes.c_float)[0] = s
+        _arr(n_used, 1, ctypes.c_int64)[0] = n
+        return 0
+
+    def u2pl_upce_backward(self, low, target, B, C, h, w, H, W, ignore, scale, grad_low, stream):
+        x = torch.from_numpy(_arr(low, B * C * h * w, ctypes.c_float).reshape(B, C, h, w).copy()).double()
+        x.requires_grad_(True)
+        t = torch.from_numpy(_arr(target, B * H * W, ctypes.c_int64).reshape(B, H, W).copy())
+        with torch.enable_grad():                              # called from inside an autograd backward
+            up = F.interpolate(x, (H, W), mode="bilinear", align_corners=True)
+            loss = F.cross_entropy(up, t, ignore_index=ignore, reduction="sum") * float(_arr(scale, 1, ctypes.c_float)[0])
+            loss.backward()
+        _arr(grad_low, B * C * h * w, ctypes.c_float).reshape(B, C, h, w)[:] = x.grad.float().numpy()
+        return 0
+
     def u2pl_ce_forward(self, logits, target, B, C, HW, ignore, nll, n_used, ws, ws_bytes, stream):
         x = _arr(logits, B * C * HW, ctypes.c_float).reshape(B, C, HW)
         t = _arr(target, B * HW, ctypes.c_int64).reshape(B, HW)

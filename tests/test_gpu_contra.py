@@ -105,8 +105,10 @@ def test_contra_matches_reference_rng_stream(golden):
     contra.forget_banks()
 
 
-def test_contra_large_random_vs_oracle():
-    """Bigger, D=256, genuine one-hot labels on every image, bank wrap-around, 3 steps."""
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_contra_large_random_vs_oracle(channels_last):
+    """Bigger, D=256, genuine one-hot labels on every image, bank wrap-around, 3 steps.  channels_last: the network's
+    own layout (register-accumulating prototype kernel, strided key / anchor gathers)."""
     from u2pl_b200 import contra
     rng = np.random.default_rng(77)
     Bl = Bu = 3
@@ -132,10 +134,13 @@ def test_contra_large_random_vs_oracle():
         rep_np = rng.standard_normal((Bl + Bu, D, h, w)).astype(np.float32)
         rept_np = rng.standard_normal((Bl + Bu, D, h, w)).astype(np.float32)
         args = (onehot[:Bl], onehot[Bl:], prob[:Bl], prob[Bl:], low, high)
-        rep = _dev(rep_np).requires_grad_(True)
+        rep, rep_t = _dev(rep_np), _dev(rept_np)
+        if channels_last:
+            rep, rep_t = rep.contiguous(memory_format=torch.channels_last), rep_t.contiguous(memory_format=torch.channels_last)
+        rep.requires_grad_(True)
         torch.manual_seed(5 + s)
         new_keys, loss, plan = contra.compute_contra_memobank_loss(
-            rep, *[_dev(a) for a in args], cfg, memobank, ptrs, qsize, _dev(rept_np), return_plan=True)
+            rep, *[_dev(a) for a in args], cfg, memobank, ptrs, qsize, rep_t, return_plan=True)
         loss.backward()
         torch.manual_seed(5 + s)
         out = port.compute_contra_memobank_loss(rep_np, *args, cfg, o_bank, o_ptr, qsize, rept_np, want_grad=True)

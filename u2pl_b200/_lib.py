@@ -27,6 +27,11 @@ SIGNATURES = {
                                              _P, _P, _P, _P, _P, _P, _P, c_size_t, _S]),
     "u2pl_partition_target": (c_int, [_P, _P, c_int64, c_int64, _P, c_int, _P, _P, _S]),
     "u2pl_entropy_masks": (c_int, [_P, _P, _P, c_int64, c_int64, _P, c_int, c_int, _P, _P, _S]),
+    "u2pl_upsample_fused_supported": (c_int, [c_int64]),
+    "u2pl_upce_ws_bytes": (c_size_t, []),
+    "u2pl_up_softmax_max": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _S]),
+    "u2pl_upce_forward": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_size_t, _S]),
+    "u2pl_upce_backward": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _S]),
     "u2pl_ce_ws_bytes": (c_size_t, [c_int64, c_int64]),
     "u2pl_ce_forward": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_size_t, _S]),
     "u2pl_ce_backward": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _S]),

@@ -290,6 +290,48 @@ proto_partial_kernel(const float *__restrict__ feat, long long sn, long long sd,
     for (uint32_t j = threadIdx.x; j < C * D; j += 256) out[j] = acc[j];
 }
 
+// Channels-last features (sd == 1, D == 256): thread d owns channel d and keeps the C class sums in REGISTERS; a pixel's
+// 256 features are one coalesced 1 KB (fp32) / 512 B (bf16) row read straight from the network's output tensor, members are
+// found from a broadcast word of the class bitmask, and the per-class adds are predicated register operations.  The shared-
+// memory read-modify-write form above serialises on LDS->FADD->STS chains (1.6 ms per V16 step with the reference's
+// multi-hot slot-0 labels: ~17 classes per member pixel); this one is bound by the member rows it reads.  Same fixed
+// summation order per (block, channel): pixels ascending -> deterministic.
+template <int C, typename T>
+__global__ void __launch_bounds__(256)
+proto_partial_cl_kernel(const T *__restrict__ feat, long long sn, long long sp, uint32_t hw, uint32_t P,
+                        const uint32_t *__restrict__ lv_bits, float *__restrict__ partial)
+{
+    constexpr uint32_t D = 256;
+    __shared__ uint32_t s_bits[2][32];
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+    const uint32_t ntiles = (P + 31) / 32;
+    const uint32_t d = threadIdx.x;
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {       // round-robin (see proto_partial_kernel)
+        uint32_t *sb = s_bits[it & 1];
+        if (threadIdx.x < 32) {
+            const uint32_t pix = t * 32 + threadIdx.x;
+            sb[threadIdx.x] = pix < P ? __ldg(lv_bits + pix) : 0u;
+        }
+        __syncthreads();                                   // double-buffered: one barrier per tile
+#pragma unroll 4
+        for (int px = 0; px < 32; ++px) {
+            const uint32_t b = sb[px];
+            if (!b) continue;
+            const uint32_t pix = t * 32 + px;
+            const uint32_t n = pix / hw, q = pix - n * hw;
+            const float v = static_cast<float>(feat[static_cast<long long>(n) * sn + static_cast<long long>(q) * sp + d]);
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] += ((b >> c) & 1u) ? v : 0.0f;
+        }
+    }
+    float *out = partial + static_cast<size_t>(blockIdx.x) * C * D;
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[c * D + d] = acc[c];
+}
+
 __global__ void __launch_bounds__(256)
 proto_reduce_kernel(const float *__restrict__ partial, int nparts, uint32_t C, uint32_t D,
                     const uint32_t *__restrict__ lv_totals, float *__restrict__ proto)
@@ -775,6 +817,10 @@ extern "C" int u2pl_contra_proto(const float *rep_teacher, int64_t sn, int64_t s
         if (e != cudaSuccess) { set_error("contra_proto: shared memory request too large"); return static_cast<int>(e); }
         configured = smem;
     }
+    if (sd == 1 && D == 256 && (C == 19 || C == 21)) {    // channels-last network output: register-accumulating kernel
+        if (C == 19) proto_partial_cl_kernel<19, float><<<parts, 256, 0, s>>>(rep_teacher, sn, sp, static_cast<uint32_t>(hw), static_cast<uint32_t>(P), lv_bits, partial);
+        else proto_partial_cl_kernel<21, float><<<parts, 256, 0, s>>>(rep_teacher, sn, sp, static_cast<uint32_t>(hw), static_cast<uint32_t>(P), lv_bits, partial);
+    } else
     proto_partial_kernel<<<parts, 256, smem, s>>>(rep_teacher, sn, sd, sp, static_cast<uint32_t>(hw), static_cast<uint32_t>(P),
                                                   static_cast<uint32_t>(C), static_cast<uint32_t>(D), lv_bits, partial);
     proto_reduce_kernel<<<static_cast<int>((C * D + 255) / 256), 256, 0, s>>>(partial, parts, static_cast<uint32_t>(C),

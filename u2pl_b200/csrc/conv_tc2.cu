@@ -22,6 +22,7 @@
 // the LEADER's `full` barrier (peer producer arrives remotely), tcgen05.commit.multicast frees the stage in both CTAs
 // and publishes the accumulator to both epilogues; both epilogues release the accumulator stage on the leader's
 // `tmem_empty` barrier.
+#include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -414,6 +415,11 @@ int conv_tc2_launch(const void *x, const void *wgt, void *out, int64_t n, int64_
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             max_clusters = sms / 2;
         }
+        if (const char *e = getenv("U2PL_CONV2_CLUSTERS")) {           // A/B override of the persistent grid (clusters)
+            const int v = atoi(e);
+            if (v > 0) max_clusters = v;
+        }
+        if (getenv("U2PL_CONV_DEBUG")) fprintf(stderr, "[conv_tc2] clusters resident: %d (smem %zu B/CTA)\n", max_clusters, smem);
         configured = true;
     }
     const long long tiles_m = static_cast<long long>(p.Nimg) * p.tiles_h * p.tiles_w;

@@ -38,6 +38,7 @@ struct SelState {
     float    val[kMaxT];            //                 exact order statistics
     uint32_t band[kMaxT];           //                 candidate band (list / counter index) of every target
     uint32_t bar;                   // fused chain: grid-barrier arrival counter (zeroed with the rest of the state)
+    unsigned long long stamp[8];    // fused chain: %globaltimer of CTA 0 at the phase boundaries (U2PL_CHAIN_TIMING=1 prints them)
 };
 
 struct Percents { float q[kMaxQ]; int use_rank; uint32_t rank; };   // use_rank: one explicit order statistic instead
@@ -767,6 +768,15 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
 constexpr int kChainThreads = 1024;
 constexpr int kChainMaxSlice = 36864;                     // keys per CTA: 144 KB of the 227 KB
 
+__device__ __forceinline__ void phase_stamp(SelState *st, int k)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        st->stamp[k] = t;
+    }
+}
+
 __device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t goal)
 {
     __syncthreads();
@@ -822,6 +832,7 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
     const uint32_t cnt = (base < N) ? min(slice, N - base) : 0u;
 
     // ---------------------------------------------------------------- P1
+    phase_stamp(st, 0);
     for (int j = tid; j < kBins1; j += kChainThreads) s_h1[j] = 0;
     __syncthreads();
     for (uint32_t j = tid; j < cnt; j += kChainThreads) {
@@ -842,7 +853,9 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
     __syncthreads();
     for (int j = tid; j < kBins1; j += kChainThreads)
         if (s_h1[j]) atomicAdd(&hist1[j], s_h1[j]);
+    phase_stamp(st, 1);
     grid_barrier(&st->bar, G);
+    phase_stamp(st, 2);
 
     // ---------------------------------------------------------------- P2: select1 (thread t owns bins 4t..4t+3)
     {
@@ -917,6 +930,7 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             if (s_h2[j]) atomicAdd(&hist2[j], s_h2[j]);
     }
     grid_barrier(&st->bar, 2 * G);
+    phase_stamp(st, 3);
 
     // ---------------------------------------------------------------- P3: 22-bit bins, bands, candidates
     if (n_all != 0) {
@@ -1017,11 +1031,12 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
         if (tid < U && s_below[tid]) atomicAdd(&st->below[tid], s_below[tid]);
     }
     grid_barrier(&st->bar, 3 * G);
+    phase_stamp(st, 4);
 
-    // ---------------------------------------------------------------- P4: exact select, CTA t < T
-    if (n_all != 0 && static_cast<int>(blockIdx.x) < T) {
-        const int t = blockIdx.x;
+    // ---------------------------------------------------------------- P4: exact select, target t on CTA t mod G
+    for (int t = blockIdx.x; n_all != 0 && t < T; t += static_cast<int>(G)) {       // (grids smaller than T loop)
         uint32_t *hist = s_h1;                             // [2048]
+        __syncthreads();
         const uint32_t u = s_band[t];
         const uint32_t n = __ldcg(&st->cnt[u]);
         const uint32_t r0 = s_grank[t] - __ldcg(&st->below[u]);           // unsigned: a violated invariant shows as r0 >= n
@@ -1056,6 +1071,7 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
         }
     }
     grid_barrier(&st->bar, 4 * G);
+    phase_stamp(st, 5);
 
     // ---------------------------------------------------------------- P5: thresholds + partition of the slice
     if (tid == 0) {
@@ -1096,6 +1112,7 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             if (s2) atomicAdd(n_kept, s2);
         }
     }
+    phase_stamp(st, 6);
 }
 
 // ------------------------------------------------------------------ OHEM (loss_helper.py:502-531)
@@ -1398,6 +1415,16 @@ static int launch_chain(const float *logits, const int64_t *target_in, uint32_t 
                                                 args, smem, s);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
     *launched = true;
+    static const bool timing = getenv("U2PL_CHAIN_TIMING") != nullptr;
+    if (timing) {                                          // debug only: synchronises the stream
+        SelState h;
+        cudaStreamSynchronize(s);
+        cudaMemcpy(&h, w.st, sizeof(SelState), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[entropy_chain] grid %u slice %u | P1 %.1f us | bar1 %.1f | P2+bar2 %.1f | P3+bar3 %.1f | P4+bar4 %.1f | P5 %.1f | total %.1f us (CTA 0)\n",
+                grid, slice, (h.stamp[1] - h.stamp[0]) * 1e-3, (h.stamp[2] - h.stamp[1]) * 1e-3, (h.stamp[3] - h.stamp[2]) * 1e-3,
+                (h.stamp[4] - h.stamp[3]) * 1e-3, (h.stamp[5] - h.stamp[4]) * 1e-3, (h.stamp[6] - h.stamp[5]) * 1e-3,
+                (h.stamp[6] - h.stamp[0]) * 1e-3);
+    }
     return check_launch("entropy_chain");
 }
 

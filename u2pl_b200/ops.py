@@ -226,6 +226,90 @@ def unsup_loss(predict, target, percent, pred_teacher, ignore=255):
     return _UnsupCE.apply(predict, target, n_kept, ignore)
 
 
+# --------------------------------------------------------------------------- fused x4 bilinear up-sampling consumers
+def upsample_fused_supported(num_classes):
+    return bool(_lib.load().u2pl_upsample_fused_supported(int(num_classes)))
+
+
+def _low(pred_low):
+    """Low-resolution logits as the kernels read them: fp32 NCHW contiguous (22 MB for V16 -- the small tensor is
+    converted, the 354 MB full-resolution one is never built)."""
+    return pred_low.detach().float().contiguous()
+
+
+def up_softmax_max(pred_low, size):
+    """torch.max(F.softmax(F.interpolate(pred_low, size, mode="bilinear", align_corners=True), dim=1), dim=1)
+    (train_semi.py:318-324) in one kernel: returns (max probability fp32 [B,H,W], arg-max int64 [B,H,W])."""
+    _need_cuda(pred_low)
+    lib = _lib.load()
+    low = _low(pred_low)
+    B, C, h, w = low.shape
+    H, W = size
+    prob = torch.empty((B, H, W), dtype=torch.float32, device=low.device)
+    label = torch.empty((B, H, W), dtype=torch.int64, device=low.device)
+    rc = lib.u2pl_up_softmax_max(_p(low), B, C, h, w, H, W, _p(prob), _p(label), _stream())
+    _lib.check(rc, "u2pl_up_softmax_max")
+    return prob, label
+
+
+class _UpCE(torch.autograd.Function):
+    """F.cross_entropy(F.interpolate(pred_low, (H,W), bilinear, align_corners=True), target, ignore_index) with the
+    gradient delivered directly at low resolution (csrc/upsample_ce.cu).  mode "mean": nll / #valid
+    (loss_helper.py:313-319).  mode "unsup": (B*H*W / n_kept) * nll / n_kept on an already partitioned target
+    (loss_helper.py:44-46)."""
+
+    @staticmethod
+    def forward(ctx, pred_low, target, n_kept, ignore):
+        _need_cuda(pred_low, target, n_kept)
+        lib = _lib.load()
+        low = _low(pred_low)
+        B, C, h, w = low.shape
+        H, W = target.shape[1:]
+        assert target.is_contiguous() and target.dtype == torch.int64 and target.shape[0] == B
+        dev = low.device
+        nll = torch.empty((), dtype=torch.float32, device=dev)
+        n_used = torch.empty((), dtype=torch.int64, device=dev)
+        ws = _workspace("upce", lib.u2pl_upce_ws_bytes(), dev)
+        rc = lib.u2pl_upce_forward(_p(low), _p(target), B, C, h, w, H, W, int(ignore), _p(nll), _p(n_used),
+                                   _p(ws), ws.numel(), _stream())
+        _lib.check(rc, "u2pl_upce_forward")
+        ctx.ignore, ctx.geom, ctx.in_dtype, ctx.unsup = ignore, (B, C, h, w, H, W), pred_low.dtype, n_kept is not None
+        if n_kept is None:
+            ctx.save_for_backward(low, target, n_used)
+            return nll / n_used.to(torch.float32)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        rc = lib.u2pl_unsup_finalize(_p(nll), _p(n_kept), target.numel(), None, _p(loss), None, _stream())
+        _lib.check(rc, "u2pl_unsup_finalize")
+        ctx.save_for_backward(low, target, n_kept, nll)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        B, C, h, w, H, W = ctx.geom
+        gout = gout.to(torch.float32).contiguous()
+        if ctx.unsup:
+            low, target, n_kept, nll = ctx.saved_tensors
+            scale = torch.empty(1, dtype=torch.float32, device=low.device)
+            rc = lib.u2pl_unsup_finalize(_p(nll), _p(n_kept), target.numel(), _p(gout), None, _p(scale), _stream())
+            _lib.check(rc, "u2pl_unsup_finalize(bwd)")
+        else:
+            low, target, n_used = ctx.saved_tensors
+            scale = (gout / n_used.to(torch.float32)).reshape(1).contiguous()
+        grad = torch.empty_like(low)
+        rc = lib.u2pl_upce_backward(_p(low), _p(target), B, C, h, w, H, W, int(ctx.ignore), _p(scale), _p(grad), _stream())
+        _lib.check(rc, "u2pl_upce_backward")
+        return grad.to(ctx.in_dtype), None, None, None
+
+
+def upsampled_ce_mean(pred_low, target, ignore=255):
+    return _UpCE.apply(pred_low, target.contiguous(), None, ignore)
+
+
+def upsampled_unsup_ce(pred_low, target_partitioned, n_kept, ignore=255):
+    return _UpCE.apply(pred_low, target_partitioned, n_kept, ignore)
+
+
 # --------------------------------------------------------------------------- A8 helpers
 def label_onehot(inputs, num_segments, ignore=255):
     """utils.py:50-59 with its scatter quirk (Q8): slot 0 = union of all images' classes (ignored

@@ -40,6 +40,11 @@ class SemiStep:
             from .u2pl.dataset.augmentation import generate_unsup_data
         self.generate_unsup_data = generate_unsup_data
         self.last = {}
+        # x4 bilinear up-sampling fused into its consumers (csrc/upsample_ce.cu) when the class count is specialised;
+        # U2PL_FUSED_UP=0 restores the ATen interpolate + full-resolution kernels (A/B runs, parity tests)
+        import os
+        self.fused_up = (os.environ.get("U2PL_FUSED_UP", "1") == "1"
+                         and ops.upsample_fused_supported(cfg["net"]["num_classes"]))
 
     # ------------------------------------------------------------------ helpers
     def _net(self, net, x):
@@ -100,8 +105,12 @@ class SemiStep:
             ph = self._event()
             teacher.eval()
             with torch.no_grad():
-                pred_u_teacher = self._up(self._net(teacher, image_u)["pred"], (h, w))
-                logits_u_aug, label_u_aug = torch.max(F.softmax(pred_u_teacher, dim=1), dim=1)
+                pred_t1 = self._net(teacher, image_u)["pred"]
+                if self.fused_up:                                             # bilinear + softmax + max in one kernel
+                    logits_u_aug, label_u_aug = ops.up_softmax_max(pred_t1, (h, w))
+                else:
+                    pred_u_teacher = self._up(pred_t1, (h, w))
+                    logits_u_aug, label_u_aug = torch.max(F.softmax(pred_u_teacher, dim=1), dim=1)
             ph = self._phase(ph, "t1")
             # ---- strong augmentation (:326-337)
             if np.random.uniform(0, 1) < 0.5 and trainer["unsupervised"].get("apply_aug", False):
@@ -114,11 +123,17 @@ class SemiStep:
             num_labeled = len(image_l)
             outs = self._net(model, torch.cat((image_l, image_u_aug)))
             pred_all, rep_all = outs["pred"], outs["rep"]
-            pred_l_large = self._up(pred_all[:num_labeled], (h, w))
-            pred_u_large = self._up(pred_all[num_labeled:], (h, w))
+            sup_lowres = self.fused_up and hasattr(self.sup_loss_fn, "forward_lowres")
+            if not sup_lowres:
+                pred_l_large = self._up(pred_all[:num_labeled], (h, w))
+            if not self.fused_up:
+                pred_u_large = self._up(pred_all[num_labeled:], (h, w))
             ph = self._phase(ph, "student_fwd")
             # ---- supervised loss (:352-358)
-            if has_aux:
+            if sup_lowres:                                                    # CE (+aux): up-sampling fused into the loss
+                sup_loss = self.sup_loss_fn.forward_lowres(
+                    [pred_all[:num_labeled], outs["aux"][:num_labeled]] if has_aux else pred_all[:num_labeled], label_l)
+            elif has_aux:
                 aux = self._up(outs["aux"][:num_labeled], (h, w))
                 sup_loss = self.sup_loss_fn([pred_l_large, aux], label_l.clone())
             else:
@@ -144,7 +159,11 @@ class SemiStep:
             ev = self._event()                                                 # one launch: loss_helper.py:35-44 + :402-415
             ent, thresh, _, target, n_kept, _ = ops.entropy_partition(pred_u_large_teacher, label_u_aug, percents, 0)
             self._event(ev, "entropy_partition")
-            unsup_loss = ops.unsup_ce(pred_u_large, target, n_kept) * trainer["unsupervised"].get("loss_weight", 1)
+            if self.fused_up:
+                unsup_loss = ops.upsampled_unsup_ce(pred_all[num_labeled:], target, n_kept)
+            else:
+                unsup_loss = ops.unsup_ce(pred_u_large, target, n_kept)
+            unsup_loss = unsup_loss * trainer["unsupervised"].get("loss_weight", 1)
             if cfg_contra:
                 if cfg_contra.get("binary", False):
                     raise NotImplementedError("compute_binary_memobank_loss is undefined in the reference itself "

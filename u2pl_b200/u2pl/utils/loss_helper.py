@@ -57,6 +57,15 @@ class Criterion(nn.Module):
         assert preds.shape[2:] == target.shape[1:]
         return _ops.cross_entropy_mean(preds, target, self._ignore_index)
 
+    def forward_lowres(self, preds_low, target):
+        """Extension used by u2pl_b200.step.SemiStep only: the same loss from the LOW-resolution logits, the x4 bilinear
+        up-sampling of train_semi.py:344-358 fused into the loss kernels (the 354 MB up-sampled tensor is never built)."""
+        if self._aux_weight > 0:
+            main_low, aux_low = preds_low
+            return (_ops.upsampled_ce_mean(main_low, target, self._ignore_index)
+                    + self._aux_weight * _ops.upsampled_ce_mean(aux_low, target, self._ignore_index))
+        return _ops.upsampled_ce_mean(preds_low, target, self._ignore_index)
+
 
 class OhemCrossEntropy2dTensor(nn.Module):
     """Online hard example mining CE -- reference loss_helper.py:451-531 (use_weight=False, reduce=False)."""
