@@ -29,7 +29,7 @@ def test_driver_imports_resolve():
 def test_synthetic_loaders_have_the_driver_shape():
     u2pl_b200.install()
     from u2pl.dataset.builder import get_loader
-    cfg = {"dataset": {"type": "pascal_semi", "batch_size": 2, "n_sup": 6, "ignore_label": 255,
+    cfg = {"dataset": {"type": "pascal_semi", "batch_size": 2, "n_sup": 6, "ignore_label": 255, "synthetic": True,
                        "train": {"crop": {"size": [33, 41]}}, "val": {"crop": {"size": [33, 41]}}},
            "net": {"num_classes": 21}}
     sup, unsup, val = get_loader(cfg, seed=3)
@@ -42,3 +42,8 @@ def test_synthetic_loaders_have_the_driver_shape():
     image_u, _ = iter(unsup).next()
     assert not torch.equal(image_u, image)
     assert len(get_loader({**cfg, "dataset": {**cfg["dataset"], "type": "pascal"}})) == 2
+    # synthetic crops are served on request only: a config without the flag (real, mistyped or missing data_root) raises
+    import pytest
+    real = {**cfg, "dataset": {**cfg["dataset"], "synthetic": False, "train": {"data_root": "../../no/such/VOC2012", "crop": {"size": [33, 41]}}}}
+    with pytest.raises(NotImplementedError, match="synthetic"):
+        get_loader(real)

@@ -7,7 +7,9 @@ need from this module is its *shape*: `get_loader(cfg, seed)` returning (sup, un
 answer both `next(it)` and the Python-2 style `it.next()` the reference still calls (train_semi.py:281,285).
 This implementation serves SYNTHETIC crops of the configured size (images ~ N(0,1), 8x8-blocky labels with a
 10-pixel ignore border -- the generator of SURVEY.md section 8d), sharded across ranks like DistributedSampler.
-Point `dataset.train.data_root` at a real directory and it refuses, instead of silently training on noise."""
+Synthetic data is served ONLY on request (`dataset.synthetic: True` in the config, or U2PL_SYNTHETIC_DATA=1): any other
+config -- a real `data_root`, a mistyped or missing one, none at all -- raises, so an unchanged train_semi.py started from
+the wrong directory cannot silently train and validate on noise."""
 import os
 
 import torch
@@ -63,10 +65,12 @@ def _world():
 def _make(cfg, split, n, seed, with_label=True):
     ds_cfg = cfg["dataset"]
     root = ds_cfg.get(split, {}).get("data_root", "")
-    if root and os.path.isdir(root) and not ds_cfg.get("synthetic", False):
-        raise NotImplementedError("u2pl_b200 ships no real-data pipeline (out of scope, SURVEY.md C11): use the "
-                                  "reference's u2pl.dataset package for real VOC/Cityscapes data, or set "
-                                  "dataset.synthetic: True")
+    if not (ds_cfg.get("synthetic", False) or os.environ.get("U2PL_SYNTHETIC_DATA", "0") == "1"):
+        raise NotImplementedError(
+            "u2pl_b200 ships no real-data pipeline (out of scope, SURVEY.md C11) and serves synthetic crops only on "
+            "request: data_root={!r} ({}).  Use the reference's u2pl.dataset package for real VOC/Cityscapes data, or set "
+            "`dataset.synthetic: True` / U2PL_SYNTHETIC_DATA=1 to train on synthetic crops".format(
+                root, "exists" if root and os.path.isdir(root) else "missing"))
     size = ds_cfg.get(split, {}).get("crop", {}).get("size", [513, 513])
     data = SyntheticCrops(n, size, cfg["net"]["num_classes"], ds_cfg.get("ignore_label", 255), seed, with_label)
     rank, world = _world()
