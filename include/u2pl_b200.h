@@ -372,6 +372,20 @@ int u2pl_conv_wgrad_splits(int64_t n, int64_t h, int64_t w, int64_t cin, int64_t
 int u2pl_conv_wgrad_bf16_nhwc(const void *x, const void *gout, float *partial, int64_t n, int64_t h, int64_t w,
                               int64_t cin, int64_t cout, int dilation, void *stream);
 
+/* ------------------------------------------------------------------------
+ * A2  SyncBatchNorm statistics exchange over peer-mapped memory (one NVSwitch box)
+ * replaces: the all_gather / all_reduce inside nn.SyncBatchNorm (reference base.py:6-8), ~350 per training step.
+ * Every rank allocates an exchange region of u2pl_peer_region_bytes() with u2pl_shard_alloc (zero-filled), exports it
+ * through CUDA IPC and maps every peer's region with u2pl_shard_open.  u2pl_peer_allreduce_f32 then sums buf[0..n) in
+ * place across the `world` ranks in ONE single-CTA kernel: push into every peer's slot, system-scope fence + flag,
+ * wait for all flags, sum in rank order (bitwise identical on every rank).  peer_bases: HOST array of `world` device
+ * pointers (own region at index `rank`).  seq: 1, 2, 3, ... identical on all ranks (double-buffering by parity).
+ * n <= u2pl_peer_max_floats() (4096).  All ranks must issue the same sequence of calls.
+ * ---------------------------------------------------------------------- */
+int64_t u2pl_peer_region_bytes(void);
+int64_t u2pl_peer_max_floats(void);
+int u2pl_peer_allreduce_f32(float *buf, int64_t n, void *const *peer_bases, int rank, int world, uint32_t seq, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

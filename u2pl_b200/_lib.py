@@ -4,7 +4,7 @@ There is no fallback: if the library is missing or a call fails, this raises.
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libu2pl_b200.so")
@@ -66,6 +66,9 @@ SIGNATURES = {
     "u2pl_maxpool3s2_out": (c_int64, [c_int64]),
     "u2pl_maxpool3s2_forward": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, _S]),
     "u2pl_maxpool3s2_backward": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, _S]),
+    "u2pl_peer_region_bytes": (c_int64, []),
+    "u2pl_peer_max_floats": (c_int64, []),
+    "u2pl_peer_allreduce_f32": (c_int, [_P, c_int64, POINTER(c_void_p), c_int, c_int, c_uint32, _S]),
     "u2pl_bn_parts": (c_int64, []),
     "u2pl_bn_stats": (c_int, [_P, c_int64, c_int64, _P, _P, _S]),
     "u2pl_bn_finalize": (c_int, [_P, c_int64, c_double, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _S]),

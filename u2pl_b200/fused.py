@@ -77,6 +77,13 @@ def _world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+def _sync_sum_(sums):
+    """Cross-rank sum of a [2,C] statistics tensor: one single-CTA kernel over peer-mapped memory on an NVSwitch box
+    (csrc/peer_reduce.cu), torch.distributed otherwise."""
+    from .peer import allreduce_small_
+    return allreduce_small_(sums)
+
+
 def _is_cl_bf16(x):
     return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
             and x.is_contiguous(memory_format=torch.channels_last))
@@ -116,7 +123,7 @@ class _BNAct(torch.autograd.Function):
             else:                                      # statistics already accumulated by the producing conv's epilogue
                 sums = sums_in
             if sync:                                   # SyncBN: global sums; every rank holds the same number of
-                dist.all_reduce(sums)                  # pixels (same per-GPU batch and crop, as in the reference configs)
+                _sync_sum_(sums)                       # pixels (same per-GPU batch and crop, as in the reference configs)
                 count = float(M) * _world()
             mean = torch.empty(C, dtype=torch.float32, device=dev)
             invstd = torch.empty(C, dtype=torch.float32, device=dev)
@@ -148,7 +155,7 @@ class _BNAct(torch.autograd.Function):
                                                _stream()), "u2pl_bn_backward_reduce")
         dweight, dbias = sums[1].clone(), sums[0].clone()            # local sums = this rank's parameter gradients
         if sync:
-            dist.all_reduce(sums)
+            _sync_sum_(sums)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
         coef = torch.empty((3, C), dtype=torch.float32, device=dev)
@@ -304,7 +311,7 @@ def _finalize_train_bn(bn, sums, count):
     C = bn.num_features
     dev = sums.device
     if isinstance(bn, nn.SyncBatchNorm) and _world() > 1:
-        dist.all_reduce(sums)
+        _sync_sum_(sums)
         count = count * _world()
     mean, invstd = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
     scale, shift = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
