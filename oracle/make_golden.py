@@ -202,6 +202,7 @@ def gen_aug(name, seed, B, H, W, mode):
     target = torch.from_numpy(rng.integers(0, 21, (B, H, W)))
     logits = torch.from_numpy(rng.random((B, H, W)).astype(np.float32))
     np.random.seed(seed)
+    torch.manual_seed(seed)                                   # classmix draws torch.randperm (augmentation.py:488-497)
     nd, nt, nl = generate_unsup_data(data, target.clone(), logits.clone(), mode=mode)
     np.savez_compressed(os.path.join(OUT, name), data=data.numpy(), target=target.numpy().astype(np.int16),
                         logits=logits.numpy(), seed=seed, mode=mode, new_data=nd.numpy(),
@@ -257,9 +258,15 @@ def main():
     gen_ohem("ohem_c19_kth", 42, 2, 19, 32, 32, min_kept=1500, thresh=0.05)
     gen_aug("aug_cutmix", 51, 4, 33, 33, "cutmix")
     gen_aug("aug_cutout", 52, 3, 29, 35, "cutout")
+    gen_aug("aug_classmix", 53, 4, 31, 27, "classmix")
     gen_model("model_r50_c21", 61, "resnet50", 21, 2, 33, 33, False)
     gen_model("model_r50_c19_aux", 62, "resnet50", 19, 2, 41, 41, True)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "aug_classmix":       # added in round 2: regenerate this fixture alone
+        os.makedirs(OUT, exist_ok=True)
+        install_shims()
+        gen_aug("aug_classmix", 53, 4, 31, 27, "classmix")
+    else:
+        main()

@@ -117,6 +117,27 @@ def test_strong_aug_matches_reference(golden, name):
     assert np.array_equal(nl, g["new_logits"])
 
 
+@pytest.mark.parametrize("name", ["aug_cutmix", "aug_cutout", "aug_classmix"])
+def test_dropin_generate_unsup_data_matches_reference(golden, name):
+    """The DROP-IN function itself (u2pl.dataset.augmentation.generate_unsup_data of the mirror package, what
+    train_semi.py:331-337 calls) against fixtures made by running the reference's: CutMix, CutOut and ClassMix, same
+    numpy / torch RNG streams.  (Tensor ops only, so it runs on CPU tensors here and on device tensors in the step.)"""
+    import torch
+    import u2pl_b200
+    u2pl_b200.install()
+    from u2pl.dataset.augmentation import generate_unsup_data
+    g = golden(name)
+    np.random.seed(int(g["seed"]))
+    torch.manual_seed(int(g["seed"]))
+    target_in = torch.from_numpy(g["target"].astype(np.int64))
+    nd, nt, nl = generate_unsup_data(torch.from_numpy(g["data"]), target_in.clone(), torch.from_numpy(g["logits"]).clone(),
+                                     mode=str(g["mode"]))
+    assert nt.dtype == torch.int64
+    assert np.array_equal(nt.numpy(), g["new_target"].astype(np.int64))
+    assert np.array_equal(nd.numpy(), g["new_data"])
+    assert np.array_equal(nl.numpy(), g["new_logits"])
+
+
 def test_rank_matches_torch_sort():
     rng = np.random.default_rng(3)
     p = rng.random((2, 7, 5, 6)).astype(np.float32)

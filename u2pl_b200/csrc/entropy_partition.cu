@@ -768,6 +768,18 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
 constexpr int kChainThreads = 1024;
 constexpr int kChainMaxSlice = 36864;                     // keys per CTA: 144 KB of the 227 KB
 
+// Streaming read of the logits (read exactly once: do not let 354 MB push the target / entropy lines out of L2) and an
+// L2-resident read of the target, which P5 reads a second time.
+__device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }     // ld.global.cs: evict-first
+__device__ __forceinline__ int64_t ld_keep(const int64_t *p)
+{
+    uint64_t pol;
+    long long v;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 __device__ __forceinline__ void phase_stamp(SelState *st, int k)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -841,8 +853,8 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
         const float *x = logits + static_cast<size_t>(b) * C * HW + p;
         float v[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
-        const int64_t t = __ldg(target_in + i);
+        for (int c = 0; c < C; ++c) v[c] = ld_stream(x + static_cast<size_t>(c) * HW);
+        const int64_t t = ld_keep(target_in + i);
         const float h = entropy_fast_of<C>(v);
         ent[i] = h;
         const bool valid = (t != ignore);
@@ -916,13 +928,9 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             uint32_t mt = 0;
 #pragma unroll
             for (int t = 0; t < kMaxT; ++t) mt |= (hi == pre[t]) ? (1u << t) : 0u;
-            if (mt) {
+            if (mt) {                                      // 1024 sub-bins: few same-address collisions inside a warp
                 const uint32_t bin = (key >> 10) & (kBinsR - 1);
-                const uint32_t peers = __match_any_sync(__activemask(), (mt << 10) | bin);
-                if (lane == __ffs(peers) - 1) {
-                    const uint32_t c2 = __popc(peers);
-                    while (mt) { const int t = __ffs(mt) - 1; mt &= mt - 1; atomicAdd(&s_h2[t * kBinsR + bin], c2); }
-                }
+                while (mt) { const int t = __ffs(mt) - 1; mt &= mt - 1; atomicAdd(&s_h2[t * kBinsR + bin], 1u); }
             }
         }
         __syncthreads();
@@ -975,15 +983,19 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             lo[u] = (u < U) ? s_lo[u] : __uint_as_float(0xff800000u);     // -inf: never below, never inside
             hi[u] = (u < U) ? s_hi[u] : lo[u];
         }
-        uint32_t *s_pix = s_h1;                            // candidates of the current tile: slice-local index ...
-        uint8_t *s_hit = reinterpret_cast<uint8_t *>(s_h2); // ... and the bands it falls into
-        for (uint32_t tb = 0; tb < cnt; tb += kBins1) {
+        // Candidates of a chunk of <= 16384 keys are compacted first (16-bit slice-local index + band mask, 48 KB: the two
+        // histogram areas) and then re-evaluated all at once, one per thread: the ~3 us latency of an exact evaluation
+        // (21 strided loads + ~900 dependent issue slots) is paid once per chunk, not once per 4096 keys.
+        constexpr uint32_t kCandChunk = 16384;
+        uint16_t *s_pix = reinterpret_cast<uint16_t *>(s_h1);              // [16384] (s_h1 + first half of s_h2)
+        uint8_t *s_hit = reinterpret_cast<uint8_t *>(s_h1) + kCandChunk * 2;  // [16384]
+        for (uint32_t tb = 0; tb < cnt; tb += kCandChunk) {
+            __syncthreads();
             if (tid == 0) s_cnt = 0;
             __syncthreads();
-#pragma unroll
-            for (int it = 0; it < kBins1 / kChainThreads; ++it) {
-                const uint32_t j = tb + it * kChainThreads + tid;
-                const uint32_t k = (j < cnt) ? s_keys[j] : kInvalidKey;
+            const uint32_t te = min(cnt, tb + kCandChunk);
+            for (uint32_t j = tb + tid; j < te; j += kChainThreads) {
+                const uint32_t k = s_keys[j];
                 if (k == kInvalidKey) continue;
                 const float h = key_float(k);
                 uint32_t hit = 0;
@@ -994,7 +1006,7 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                 }
                 if (hit) {
                     const uint32_t pos = atomicAdd(&s_cnt, 1u);
-                    s_pix[pos] = j;
+                    s_pix[pos] = static_cast<uint16_t>(j);
                     s_hit[pos] = static_cast<uint8_t>(hit);
                 }
             }
@@ -1020,8 +1032,8 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                     lists[static_cast<size_t>(u) * N + pos] = ek;
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
 #pragma unroll
         for (int u = 0; u < kMaxT; ++u) {
             const uint32_t sm = static_cast<uint32_t>(warp_sum_i(static_cast<int>(below[u])));
@@ -1094,7 +1106,7 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
         int kept = 0;
         for (uint32_t j = tid; j < cnt; j += kChainThreads) {
             const uint32_t i = base + j;
-            const int64_t t = __ldg(target_in + i);
+            const int64_t t = ld_keep(target_in + i);
             const uint32_t key = s_keys[j];
             const bool valid = (key != kInvalidKey);
             const bool drop = valid && (key_float(key) >= th);
