@@ -362,6 +362,30 @@ class FakeLoss:
         _arr(grad_low, B * C * h * w, ctypes.c_float).reshape(B, C, h, w)[:] = x.grad.float().numpy()
         return 0
 
+    def u2pl_sgd_tensor_bytes(self):
+        return 56
+
+    def u2pl_sgd_chunk_elems(self):
+        return 8192
+
+    def u2pl_sgd_ema_step(self, tensor_table, chunk_table, n_chunks, momentum, decay, do_ema, stream):
+        import struct
+        ch = _arr(chunk_table, 2 * n_chunks, ctypes.c_uint32).reshape(-1, 2)
+        n_tensors = int(ch[:, 0].max()) + 1
+        raw = ctypes.string_at(_addr(tensor_table), 56 * n_tensors)
+        for k in range(n_tensors):
+            pp, gp, mp, tp, n, lr, wd, first, _ = struct.unpack_from("<QQQQqffii", raw, 56 * k)
+            p = _arr(ctypes.c_void_p(pp), n, ctypes.c_float)
+            g = _arr(ctypes.c_void_p(gp), n, ctypes.c_float)
+            m = _arr(ctypes.c_void_p(mp), n, ctypes.c_float)
+            d = g + np.float32(wd) * p
+            m[:] = d if first else np.float32(momentum) * m + d
+            p[:] = p - np.float32(lr) * m
+            if do_ema and tp:
+                t = _arr(ctypes.c_void_p(tp), n, ctypes.c_float)
+                t[:] = np.float32(decay) * t + np.float32(1.0 - decay) * p
+        return 0
+
     def u2pl_ce_forward(self, logits, target, B, C, HW, ignore, nll, n_used, ws, ws_bytes, stream):
         x = _arr(logits, B * C * HW, ctypes.c_float).reshape(B, C, HW)
         t = _arr(target, B * HW, ctypes.c_int64).reshape(B, HW)

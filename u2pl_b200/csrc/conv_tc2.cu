@@ -110,7 +110,10 @@ __device__ __forceinline__ void named_bar(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <bool kStats>
+// Debug timeline (U2PL_CONV2_TRACE=1): clock64 of cluster 0's producer / MMA threads at the first 128 k-blocks.
+__device__ long long g_trace[6][128];
+
+template <bool kStats, bool kTrace = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, Conv2Params p)
@@ -169,7 +172,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     const int tap = step / kb_per_tap, kb = step % kb_per_tap;
                     const int dh = (tap / p.S - p.R / 2) * p.dil, dw = (tap % p.S - p.S / 2) * p.dil;
                     const int s = it % kStages;
+                    if (kTrace && pair_id == 0 && it < 128) g_trace[rank * 2][it] = clock64();
                     mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
+                    if (kTrace && pair_id == 0 && it < 128) g_trace[rank * 2 + 1][it] = clock64();
                     const uint32_t leader_full = map_to_cta(smem_u32(full + s), 0);
                     if (rank == 0) mbar_expect_tx(full + s, 2 * kStageBytes);         // both CTAs' A tile and B half
                     else remote_arrive(leader_full);
@@ -190,7 +195,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 const uint32_t d_tmem = tmem_base + acc * kBN;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % kStages;
+                    if (kTrace && pair_id == 0 && it < 128) g_trace[4][it] = clock64();
                     mbar_wait(full + s, (it / kStages) & 1);
+                    if (kTrace && pair_id == 0 && it < 128) g_trace[5][it] = clock64();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a0 = smem_u32(sA + s * kTileBytes), b0 = smem_u32(sB + s * kTileBytes);
 #pragma unroll
@@ -426,6 +433,24 @@ int conv_tc2_launch(const void *x, const void *wgt, void *out, int64_t n, int64_
     const long long tiles = ((tiles_m + 1) / 2) * ((cout + kBN - 1) / kBN);
     const unsigned pairs = static_cast<unsigned>(tiles < max_clusters ? tiles : max_clusters);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool trace = getenv("U2PL_CONV2_TRACE") != nullptr;
+    if (trace && !stat_part) {                        // debug: timeline of cluster 0, printed after a device synchronise
+        static bool tconf = false;
+        if (!tconf) { cudaFuncSetAttribute(conv_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); tconf = true; }
+        conv_tc2_kernel<false, true><<<2 * pairs, kThreads, smem, st>>>(mx, mw, mo, mr, p);
+        cudaDeviceSynchronize();
+        static long long h[6][128];
+        cudaMemcpyFromSymbol(h, g_trace, sizeof(h));
+        static int dumps = 0;
+        if (dumps++ < 2) {
+            fprintf(stderr, "[conv_tc2 trace] cin %lld cout %lld k %d: k-block | leader producer wait-start, wait-end | MMA full wait-start, wait-end | peer producer wait-start, wait-end (leader clocks relative to leader t0; peer relative to peer t0)\n",
+                    static_cast<long long>(cin), static_cast<long long>(cout), ksize);
+            for (int i = 0; i < 40; ++i)
+                fprintf(stderr, "  %3d | %7lld %7lld | %7lld %7lld | %7lld %7lld\n", i, h[0][i] - h[0][0], h[1][i] - h[0][0], h[4][i] - h[0][0],
+                        h[5][i] - h[0][0], h[2][i] - h[2][0], h[3][i] - h[2][0]);
+        }
+        return check_launch(what);
+    }
     if (stat_part) conv_tc2_kernel<true><<<2 * pairs, kThreads, smem, st>>>(mx, mw, mo, mr, p);
     else conv_tc2_kernel<false><<<2 * pairs, kThreads, smem, st>>>(mx, mw, mo, mr, p);
     return check_launch(what);

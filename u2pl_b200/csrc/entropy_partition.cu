@@ -752,33 +752,35 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
 // ====================================================================== the whole chain as ONE cooperative kernel
 // entropy -> percentile thresholds -> reliable/unreliable partition in a single persistent launch (one 1024-thread CTA
 // per SM, cudaLaunchCooperativeKernel so that the software grid barrier below cannot deadlock).  CTA b owns the
-// contiguous pixel slice [b*slice, (b+1)*slice) and keeps that slice's order-preserving entropy keys in SHARED MEMORY
-// (<= 144 KB) from the first pass to the last, so the logits are streamed from HBM exactly once and every later pass
-// (10-bit refinement histogram, candidate band test, partition compare) reads shared memory instead of re-scanning
-// 16.8 MB of keys out of L2 from four separate launches:
-//   P1  fast entropy of the slice (coalesced, C loads in flight per thread) -> ent[], s_keys[], 12-bit histogram
-//   P2  select1 on the merged histogram (every CTA, redundantly) + 10-bit histogram of the slice's keys inside the
-//       target bins
-//   P3  22-bit bin per target rank -> candidate bands; band test on s_keys; candidates are re-evaluated under the
-//       arithmetic contract (exact value back into ent[] and s_keys[], exact key appended to the band's global list)
-//   P4  CTA t < T: exact radix select of target t inside its candidate list
-//   P5  numpy lerp -> thresholds (every CTA, redundantly; CTA 0 publishes) and the partition of the slice:
-//       target_out = (entropy >= thresh[part_idx] && valid) ? ignore : target_in, drop mask, kept count
-// Four grid barriers (~2 us each) replace four launches + four L2 scans.  Soundness argument: see the two-level path.
+// contiguous pixel slice [b*slice, (b+1)*slice) and keeps, in SHARED MEMORY from the first pass to the last, that slice's
+// order-preserving entropy keys (<= 128 KB) and class ids (1 byte per pixel): the logits are streamed from HBM exactly
+// once, the target is read once, and every later pass reads shared memory instead of re-scanning 16.8 MB of keys and
+// 33.7 MB of labels out of L2 / HBM from separate launches:
+//   P1  fast entropy of the slice (coalesced, C loads in flight per thread) -> ent[], s_keys[], s_cls[] and a FINE
+//       histogram: the top 16 key bits (sign, exponent, 7 mantissa bits = 128 bins per octave) restricted to the range
+//       an entropy can take, [2^-24, 4) -> 3328 bins + two clamp bins, 13 KB.  (A 12-bit histogram needed a second,
+//       10-bit refinement pass over the keys and one more grid barrier to reach the same resolution.)
+//   P2  every CTA (redundantly) selects the bin of each target rank from the merged histogram; a target's candidate band
+//       is its bin widened by 3*kDelta; band test on s_keys; all candidates of the slice are compacted and re-evaluated
+//       AT ONCE under the arithmetic contract (exact value back into ent[] and s_keys[], exact key appended to the band's
+//       global list); pixels surely below a band are only counted
+//   P3  CTA t mod G: exact radix select of target t inside its candidate list
+//   P4  numpy lerp -> thresholds (every CTA, redundantly; CTA 0 publishes) and the partition of the slice from shared
+//       memory: target_out = (entropy >= thresh[part_idx] && valid) ? ignore : class, drop mask, kept count
+// Three grid barriers replace four launches + three scans.  Soundness argument: see the two-level path (kDelta).
 constexpr int kChainThreads = 1024;
-constexpr int kChainMaxSlice = 36864;                     // keys per CTA: 144 KB of the 227 KB
+constexpr int kChainMaxSlice = 32768;                     // pixels per CTA: 128 KB of keys + 32 KB of class ids
+constexpr uint32_t kFineBase = 0x8000u + (103u << 7);     // key >> 16 of 2^-24
+constexpr int kFineBins = ((129 - 103) << 7) + 2;         // [2^-24, 4) at 128 bins per octave, + one clamp bin on either side
+constexpr uint32_t kCandCap = 16384;                      // candidates compacted per round (16-bit index + band mask)
 
-// Streaming read of the logits (read exactly once: do not let 354 MB push the target / entropy lines out of L2) and an
-// L2-resident read of the target, which P5 reads a second time.
-__device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }     // ld.global.cs: evict-first
-__device__ __forceinline__ int64_t ld_keep(const int64_t *p)
+__device__ __forceinline__ uint32_t fine_bin(uint32_t key)
 {
-    uint64_t pol;
-    long long v;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("ld.global.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
-    return v;
+    const uint32_t hi = key >> 16;
+    return hi < kFineBase ? 0u : min(hi - kFineBase + 1u, static_cast<uint32_t>(kFineBins - 1));
 }
+// keys of bin b are [fine_lo_key(b), fine_lo_key(b+1)); bin 0 starts at key 0, the last bin never ends
+__device__ __forceinline__ uint32_t fine_lo_key(uint32_t b) { return b == 0 ? 0u : (kFineBase + b - 1u) << 16; }
 
 __device__ __forceinline__ void phase_stamp(SelState *st, int k)
 {
@@ -802,7 +804,7 @@ __device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t goal)
     __syncthreads();
 }
 
-// block-wide exclusive scan position of `cnt` (one value per thread, 1024 threads); returns excl, total in *tot
+// block-wide exclusive scan position of `cnt` (one value per thread, 1024 threads)
 __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t cnt, uint32_t *warp_tot)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -826,16 +828,17 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                      uint32_t slice, int64_t ignore, Percents pc, int nq, int part_idx,
                      float *__restrict__ ent, float *__restrict__ thresh, int64_t *__restrict__ n_valid,
                      int64_t *__restrict__ target_out, uint8_t *__restrict__ drop_mask, unsigned long long *__restrict__ n_kept,
-                     uint32_t *__restrict__ hist1, uint32_t *__restrict__ hist2, SelState *__restrict__ st,
-                     uint32_t *__restrict__ lists)
+                     uint32_t *__restrict__ hist, SelState *__restrict__ st, uint32_t *__restrict__ lists)
 {
     extern __shared__ uint32_t chain_smem[];
     uint32_t *s_keys = chain_smem;                         // [slice]
-    uint32_t *s_h1 = s_keys + ((slice + 3u) & ~3u);        // [4096]: 12-bit histogram; later candidate staging / select histogram
-    uint32_t *s_h2 = s_h1 + kBins1;                        // [kMaxT][1024]: 10-bit histograms; later candidate band masks
-    __shared__ uint32_t warp_tot[32], s_prefix[kMaxT], s_rank[kMaxT], s_grank[kMaxT], s_pre22[kMaxT], s_band[kMaxT], s_below[kMaxT];
+    uint32_t *s_hist = s_keys + slice;                     // [kFineBins rounded to 4096]: fine histogram; later select histogram
+    uint16_t *s_pix = reinterpret_cast<uint16_t *>(s_hist + 4096);       // [kCandCap] candidate slice-local index
+    uint8_t *s_hit = reinterpret_cast<uint8_t *>(s_pix + kCandCap);      // [kCandCap] candidate band mask
+    uint8_t *s_cls = s_hit + kCandCap;                     // [slice] class id of the pixel (255 stands for every ignored one)
+    __shared__ uint32_t warp_tot[32], s_grank[kMaxT], s_tbin[kMaxT], s_band[kMaxT], s_below[kMaxT];
     __shared__ float s_gamma[kMaxQ], s_lo[kMaxT], s_hi[kMaxT], s_thr[kMaxQ];
-    __shared__ uint32_t s_n, s_cnt, s_sel_prefix, s_sel_rank;
+    __shared__ uint32_t s_n, s_cnt, s_sel_prefix, s_sel_rank, s_wide;
     __shared__ int s_nband;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = 2 * nq;
@@ -845,7 +848,8 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
 
     // ---------------------------------------------------------------- P1
     phase_stamp(st, 0);
-    for (int j = tid; j < kBins1; j += kChainThreads) s_h1[j] = 0;
+    for (int j = tid; j < 4096; j += kChainThreads) s_hist[j] = 0;
+    if (tid == 0) s_wide = 0;
     __syncthreads();
     for (uint32_t j = tid; j < cnt; j += kChainThreads) {
         const uint32_t i = base + j;
@@ -853,26 +857,28 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
         const float *x = logits + static_cast<size_t>(b) * C * HW + p;
         float v[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = ld_stream(x + static_cast<size_t>(c) * HW);
-        const int64_t t = ld_keep(target_in + i);
+        for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
+        const int64_t t = __ldg(target_in + i);
         const float h = entropy_fast_of<C>(v);
         ent[i] = h;
         const bool valid = (t != ignore);
         const uint32_t key = valid ? float_key(h) : kInvalidKey;
         s_keys[j] = key;
-        if (valid) hist_add(s_h1, key >> 20);
+        s_cls[j] = valid ? static_cast<uint8_t>(t) : static_cast<uint8_t>(255);
+        if (valid && (t < 0 || t > 254)) s_wide = 1;       // a label that one byte cannot hold: P4 re-reads target_in
+        if (valid) hist_add(s_hist, fine_bin(key));
     }
     __syncthreads();
-    for (int j = tid; j < kBins1; j += kChainThreads)
-        if (s_h1[j]) atomicAdd(&hist1[j], s_h1[j]);
+    for (int j = tid; j < kFineBins; j += kChainThreads)
+        if (s_hist[j]) atomicAdd(&hist[j], s_hist[j]);
     phase_stamp(st, 1);
     grid_barrier(&st->bar, G);
     phase_stamp(st, 2);
 
-    // ---------------------------------------------------------------- P2: select1 (thread t owns bins 4t..4t+3)
+    // ---------------------------------------------------------------- P2: bins of the target ranks, bands, candidates
     {
-        const uint4 q = __ldcg(reinterpret_cast<const uint4 *>(hist1) + tid);
-        const uint32_t loc[4] = {q.x, q.y, q.z, q.w};
+        const uint4 q = (tid * 4 < 4096) ? __ldcg(reinterpret_cast<const uint4 *>(hist) + tid) : make_uint4(0, 0, 0, 0);
+        const uint32_t loc[4] = {q.x, q.y, q.z, q.w};      // thread t owns bins 4t..4t+3 (the global array is padded to 4096)
         const uint32_t sum = loc[0] + loc[1] + loc[2] + loc[3];
         const uint32_t excl = block_excl_scan_1024(sum, warp_tot);
         if (tid == kChainThreads - 1) s_n = excl + sum;
@@ -901,7 +907,7 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                     uint32_t cum = excl;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        if (r < cum + loc[j]) { s_prefix[t] = tid * 4 + j; s_rank[t] = r - cum; break; }
+                        if (r < cum + loc[j]) { s_tbin[t] = tid * 4 + j; break; }
                         cum += loc[j];
                     }
                 }
@@ -911,64 +917,23 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
     }
     const uint32_t n_all = s_n;                            // uniform across the grid (same histogram everywhere)
     if (n_all != 0) {
-        for (int j = tid; j < T * kBinsR; j += kChainThreads) s_h2[j] = 0;
-        uint32_t pre[kMaxT];                               // targets with equal prefixes share the first one's histogram
-#pragma unroll
-        for (int t = 0; t < kMaxT; ++t) {
-            pre[t] = (t < T) ? s_prefix[t] : kInvalidKey;
-#pragma unroll
-            for (int u = 0; u < t; ++u)
-                if (t < T && s_prefix[u] == s_prefix[t]) pre[t] = kInvalidKey;
-        }
-        __syncthreads();
-        for (uint32_t j = tid; j < cnt; j += kChainThreads) {
-            const uint32_t key = s_keys[j];
-            if (key == kInvalidKey) continue;
-            const uint32_t hi = key >> 20;
-            uint32_t mt = 0;
-#pragma unroll
-            for (int t = 0; t < kMaxT; ++t) mt |= (hi == pre[t]) ? (1u << t) : 0u;
-            if (mt) {                                      // 1024 sub-bins: few same-address collisions inside a warp
-                const uint32_t bin = (key >> 10) & (kBinsR - 1);
-                while (mt) { const int t = __ffs(mt) - 1; mt &= mt - 1; atomicAdd(&s_h2[t * kBinsR + bin], 1u); }
-            }
-        }
-        __syncthreads();
-        for (int j = tid; j < T * kBinsR; j += kChainThreads)
-            if (s_h2[j]) atomicAdd(&hist2[j], s_h2[j]);
-    }
-    grid_barrier(&st->bar, 2 * G);
-    phase_stamp(st, 3);
-
-    // ---------------------------------------------------------------- P3: 22-bit bins, bands, candidates
-    if (n_all != 0) {
-        for (int t = 0; t < T; ++t) {                      // thread j owns sub-bin j of target t's histogram
-            int owner = t;
-            for (int u = t - 1; u >= 0; --u) if (s_prefix[u] == s_prefix[t]) owner = u;
-            const uint32_t c2 = __ldcg(hist2 + owner * kBinsR + tid);
-            const uint32_t excl = block_excl_scan_1024(c2, warp_tot);
-            const uint32_t r = s_rank[t];
-            if (r >= excl && r < excl + c2) s_pre22[t] = (s_prefix[t] << 10) | static_cast<uint32_t>(tid);
-        }
-        __syncthreads();
         if (tid == 0) {                                    // merge targets with the same bin into one candidate band
             int nb = 0;
             for (int t = 0; t < T; ++t) {
                 int b = -1;
-                for (int u = 0; u < t; ++u) if (s_pre22[u] == s_pre22[t]) { b = static_cast<int>(s_band[u]); break; }
+                for (int u = 0; u < t; ++u) if (s_tbin[u] == s_tbin[t]) { b = static_cast<int>(s_band[u]); break; }
                 if (b < 0) {
                     b = nb++;
-                    const uint32_t p22 = s_pre22[t];
-                    s_lo[b] = key_float(p22 << 10) - 3.0f * kDelta;
-                    s_hi[b] = (p22 == 0x3FFFFFu) ? __uint_as_float(0x7f800000u) : key_float((p22 + 1u) << 10) + 3.0f * kDelta;
+                    const uint32_t bin = s_tbin[t];
+                    s_lo[b] = (bin == 0) ? __uint_as_float(0xff800000u) : key_float(fine_lo_key(bin)) - 3.0f * kDelta;
+                    s_hi[b] = (bin == kFineBins - 1) ? __uint_as_float(0x7f800000u) : key_float(fine_lo_key(bin + 1)) + 3.0f * kDelta;
                 }
                 s_band[t] = static_cast<uint32_t>(b);
-                if (blockIdx.x == 0) st->band[t] = static_cast<uint32_t>(b);
             }
             s_nband = nb;
             if (blockIdx.x == 0) {
                 st->n = n_all;
-                for (int t = 0; t < T; ++t) st->grank[t] = s_grank[t];
+                for (int t = 0; t < T; ++t) { st->grank[t] = s_grank[t]; st->band[t] = s_band[t]; }
                 for (int j = 0; j < nq; ++j) st->gamma[j] = s_gamma[j];
             }
         }
@@ -980,20 +945,24 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
 #pragma unroll
         for (int u = 0; u < kMaxT; ++u) {
             below[u] = 0;
-            lo[u] = (u < U) ? s_lo[u] : __uint_as_float(0xff800000u);     // -inf: never below, never inside
+            lo[u] = (u < U) ? s_lo[u] : __uint_as_float(0x7f800000u);     // +inf: nothing is inside, everything "below" (unused)
             hi[u] = (u < U) ? s_hi[u] : lo[u];
         }
-        // Candidates of a chunk of <= 16384 keys are compacted first (16-bit slice-local index + band mask, 48 KB: the two
-        // histogram areas) and then re-evaluated all at once, one per thread: the ~3 us latency of an exact evaluation
-        // (21 strided loads + ~900 dependent issue slots) is paid once per chunk, not once per 4096 keys.
-        constexpr uint32_t kCandChunk = 16384;
-        uint16_t *s_pix = reinterpret_cast<uint16_t *>(s_h1);              // [16384] (s_h1 + first half of s_h2)
-        uint8_t *s_hit = reinterpret_cast<uint8_t *>(s_h1) + kCandChunk * 2;  // [16384]
-        for (uint32_t tb = 0; tb < cnt; tb += kCandChunk) {
+        // Candidates are compacted (16-bit slice-local index + band mask) and then re-evaluated all at once, one per
+        // thread, so the ~3 us latency of an exact evaluation (C strided loads + ~900 dependent issue slots) is paid once.
+        // A slice holding more than kCandCap candidates (massive ties) is processed in several rounds of kCandCap keys.
+        for (uint32_t tb = 0; tb < cnt; ) {
             __syncthreads();
             if (tid == 0) s_cnt = 0;
             __syncthreads();
-            const uint32_t te = min(cnt, tb + kCandChunk);
+            // a round covers as many keys as can never overflow the staging area: everything when the slice is small,
+            // else kCandCap keys (the common case has a few hundred candidates; one round = the whole slice is attempted
+            // first and kept if it fits)
+            const bool whole = (tb == 0);
+            const uint32_t te = whole ? cnt : min(cnt, tb + kCandCap);
+            uint32_t below_r[kMaxT];
+#pragma unroll
+            for (int u = 0; u < kMaxT; ++u) below_r[u] = 0;
             for (uint32_t j = tb + tid; j < te; j += kChainThreads) {
                 const uint32_t k = s_keys[j];
                 if (k == kInvalidKey) continue;
@@ -1001,17 +970,47 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                 uint32_t hit = 0;
 #pragma unroll
                 for (int u = 0; u < kMaxT; ++u) {
-                    below[u] += (h < lo[u]) ? 1u : 0u;
-                    hit |= (h >= lo[u] && h < hi[u]) ? (1u << u) : 0u;
+                    below_r[u] += (u < U && h < lo[u]) ? 1u : 0u;
+                    hit |= (u < U && h >= lo[u] && h < hi[u]) ? (1u << u) : 0u;
                 }
                 if (hit) {
                     const uint32_t pos = atomicAdd(&s_cnt, 1u);
-                    s_pix[pos] = static_cast<uint16_t>(j);
-                    s_hit[pos] = static_cast<uint8_t>(hit);
+                    if (pos < kCandCap) { s_pix[pos] = static_cast<uint16_t>(j); s_hit[pos] = static_cast<uint8_t>(hit); }
                 }
             }
             __syncthreads();
-            const uint32_t nc = s_cnt;
+            uint32_t nc = s_cnt;
+            if (whole && nc > kCandCap) {                  // did not fit: redo this stretch in bounded rounds
+                __syncthreads();
+                if (tid == 0) s_cnt = 0;
+                __syncthreads();
+                const uint32_t te2 = min(cnt, tb + kCandCap);
+#pragma unroll
+                for (int u = 0; u < kMaxT; ++u) below_r[u] = 0;
+                for (uint32_t j = tb + tid; j < te2; j += kChainThreads) {
+                    const uint32_t k = s_keys[j];
+                    if (k == kInvalidKey) continue;
+                    const float h = key_float(k);
+                    uint32_t hit = 0;
+#pragma unroll
+                    for (int u = 0; u < kMaxT; ++u) {
+                        below_r[u] += (u < U && h < lo[u]) ? 1u : 0u;
+                        hit |= (u < U && h >= lo[u] && h < hi[u]) ? (1u << u) : 0u;
+                    }
+                    if (hit) {
+                        const uint32_t pos = atomicAdd(&s_cnt, 1u);
+                        s_pix[pos] = static_cast<uint16_t>(j);
+                        s_hit[pos] = static_cast<uint8_t>(hit);
+                    }
+                }
+                __syncthreads();
+                nc = s_cnt;
+                tb = te2;
+            } else {
+                tb = te;
+            }
+#pragma unroll
+            for (int u = 0; u < kMaxT; ++u) below[u] += below_r[u];
             for (uint32_t c2 = tid; c2 < nc; c2 += kChainThreads) {       // exact (contract) entropy of the candidates
                 const uint32_t j = s_pix[c2];
                 uint32_t hit = s_hit[c2];
@@ -1042,12 +1041,12 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
         __syncthreads();
         if (tid < U && s_below[tid]) atomicAdd(&st->below[tid], s_below[tid]);
     }
-    grid_barrier(&st->bar, 3 * G);
-    phase_stamp(st, 4);
+    grid_barrier(&st->bar, 2 * G);
+    phase_stamp(st, 3);
 
-    // ---------------------------------------------------------------- P4: exact select, target t on CTA t mod G
+    // ---------------------------------------------------------------- P3: exact select, target t on CTA t mod G
     for (int t = blockIdx.x; n_all != 0 && t < T; t += static_cast<int>(G)) {       // (grids smaller than T loop)
-        uint32_t *hist = s_h1;                             // [2048]
+        uint32_t *sel = s_hist;                            // [2048]
         __syncthreads();
         const uint32_t u = s_band[t];
         const uint32_t n = __ldcg(&st->cnt[u]);
@@ -1059,17 +1058,17 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             if (tid == 0) { s_sel_prefix = 0; s_sel_rank = r0; }
             const int shifts[3] = {21, 10, 0}, nbits[3] = {11, 11, 10};
             for (int pass = 0; pass < 3; ++pass) {
-                hist[tid] = 0; hist[tid + 1024] = 0;
+                sel[tid] = 0; sel[tid + 1024] = 0;
                 __syncthreads();
                 const uint32_t pre = s_sel_prefix, r = s_sel_rank;
                 const int sh = shifts[pass], hb = sh + nbits[pass];
                 const uint32_t mask = (1u << nbits[pass]) - 1u;
                 for (uint32_t j = tid; j < n; j += kChainThreads) {
                     const uint32_t k = __ldcg(list + j);
-                    if (pass == 0 || (k >> hb) == pre) atomicAdd(&hist[(k >> sh) & mask], 1u);
+                    if (pass == 0 || (k >> hb) == pre) atomicAdd(&sel[(k >> sh) & mask], 1u);
                 }
                 __syncthreads();
-                const uint32_t c0 = hist[2 * tid], c1 = hist[2 * tid + 1], sum = c0 + c1;
+                const uint32_t c0 = sel[2 * tid], c1 = sel[2 * tid + 1], sum = c0 + c1;
                 const uint32_t excl = block_excl_scan_1024(sum, warp_tot);
                 __syncthreads();
                 if (r >= excl && r < excl + sum) {
@@ -1082,10 +1081,10 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             if (tid == 0) st->val[t] = key_float(s_sel_prefix);
         }
     }
-    grid_barrier(&st->bar, 4 * G);
-    phase_stamp(st, 5);
+    grid_barrier(&st->bar, 3 * G);
+    phase_stamp(st, 4);
 
-    // ---------------------------------------------------------------- P5: thresholds + partition of the slice
+    // ---------------------------------------------------------------- P4: thresholds + partition of the slice
     if (tid == 0) {
         for (int j = 0; j < nq; ++j) {
             float r = __uint_as_float(0x7fc00000u);
@@ -1103,14 +1102,15 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
     __syncthreads();
     if (target_out != nullptr) {
         const float th = s_thr[part_idx];
+        const bool wide = s_wide != 0;
         int kept = 0;
         for (uint32_t j = tid; j < cnt; j += kChainThreads) {
             const uint32_t i = base + j;
-            const int64_t t = ld_keep(target_in + i);
             const uint32_t key = s_keys[j];
             const bool valid = (key != kInvalidKey);
             const bool drop = valid && (key_float(key) >= th);
-            target_out[i] = drop ? ignore : t;
+            const int64_t t = (valid && !drop) ? (wide ? __ldg(target_in + i) : static_cast<int64_t>(s_cls[j])) : ignore;
+            target_out[i] = t;
             if (drop_mask) drop_mask[i] = drop ? 1 : 0;
             kept += (valid && !drop) ? 1 : 0;
         }
@@ -1124,7 +1124,7 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             if (s2) atomicAdd(n_kept, s2);
         }
     }
-    phase_stamp(st, 6);
+    phase_stamp(st, 5);
 }
 
 // ------------------------------------------------------------------ OHEM (loss_helper.py:502-531)
@@ -1406,10 +1406,11 @@ static int launch_chain(const float *logits, const int64_t *target_in, uint32_t 
     uint32_t slice = (N + grid - 1) / grid;
     slice = (slice + 3u) & ~3u;
     if (slice > static_cast<uint32_t>(kChainMaxSlice)) return 0;
-    const size_t smem = (static_cast<size_t>(slice) + kBins1 + kMaxT * kBinsR) * 4;
+    auto smem_for = [](size_t sl) { return sl * 4 + 4096 * 4 + kCandCap * 3 + sl; };
+    const size_t smem = smem_for(slice);
     static bool configured = false;
     if (!configured) {
-        const size_t max_smem = (static_cast<size_t>(kChainMaxSlice) + kBins1 + kMaxT * kBinsR) * 4;
+        const size_t max_smem = smem_for(kChainMaxSlice);
         cudaError_t e = cudaFuncSetAttribute(entropy_chain_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem));
         if (e != cudaSuccess) { cudaGetLastError(); return 0; }
         configured = true;
@@ -1421,7 +1422,7 @@ static int launch_chain(const float *logits, const int64_t *target_in, uint32_t 
     unsigned long long *nk = reinterpret_cast<unsigned long long *>(n_kept);
     uint32_t hw_ = hw, N_ = N;
     void *args[] = {&logits, &target_in, &hw_, &N_, &slice, &ignore, &pcc, &nq, &part_idx, &entropy, &thresh, &n_valid,
-                    &target_out, &drop_mask, &nk, const_cast<uint32_t **>(&w.hist1), const_cast<uint32_t **>(&w.hist2),
+                    &target_out, &drop_mask, &nk, const_cast<uint32_t **>(&w.hist1),      // hist1: 4096 words, zeroed: the fine histogram
                     const_cast<SelState **>(&w.st), &lists};
     cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(entropy_chain_kernel<C>), dim3(grid), dim3(kChainThreads),
                                                 args, smem, s);
@@ -1432,10 +1433,9 @@ static int launch_chain(const float *logits, const int64_t *target_in, uint32_t 
         SelState h;
         cudaStreamSynchronize(s);
         cudaMemcpy(&h, w.st, sizeof(SelState), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[entropy_chain] grid %u slice %u | P1 %.1f us | bar1 %.1f | P2+bar2 %.1f | P3+bar3 %.1f | P4+bar4 %.1f | P5 %.1f | total %.1f us (CTA 0)\n",
+        fprintf(stderr, "[entropy_chain] grid %u slice %u | P1 %.1f us | bar1 %.1f | P2+bar2 %.1f | P3+bar3 %.1f | P4 %.1f | total %.1f us (CTA 0)\n",
                 grid, slice, (h.stamp[1] - h.stamp[0]) * 1e-3, (h.stamp[2] - h.stamp[1]) * 1e-3, (h.stamp[3] - h.stamp[2]) * 1e-3,
-                (h.stamp[4] - h.stamp[3]) * 1e-3, (h.stamp[5] - h.stamp[4]) * 1e-3, (h.stamp[6] - h.stamp[5]) * 1e-3,
-                (h.stamp[6] - h.stamp[0]) * 1e-3);
+                (h.stamp[4] - h.stamp[3]) * 1e-3, (h.stamp[5] - h.stamp[4]) * 1e-3, (h.stamp[5] - h.stamp[0]) * 1e-3);
     }
     return check_launch("entropy_chain");
 }

@@ -45,6 +45,12 @@ class SemiStep:
         import os
         self.fused_up = (os.environ.get("U2PL_FUSED_UP", "1") == "1"
                          and ops.upsample_fused_supported(cfg["net"]["num_classes"]))
+        # SGD + EMA as one multi-tensor kernel (csrc/sgd_ema.cu); U2PL_FUSED_OPT=0 restores optimizer.step() + _foreach EMA
+        self.fused_opt = None
+        if (os.environ.get("U2PL_FUSED_OPT", "1") == "1" and isinstance(optimizer, torch.optim.SGD)
+                and all(g.get("momentum", 0) > 0 and not g.get("nesterov", False) for g in optimizer.param_groups)):
+            from .optim import FusedSGDEMA
+            self.fused_opt = FusedSGDEMA(optimizer, list(model.parameters()), list(model_teacher.parameters()))
 
     # ------------------------------------------------------------------ helpers
     def _net(self, net, x):
@@ -190,22 +196,26 @@ class SemiStep:
         self.optimizer.zero_grad()
         loss.backward()
         ph = self._phase(ph, "backward")
-        self.optimizer.step()
-
-        if epoch >= sup_only_epoch:                                           # :531-548 EMA (parameters only)
-            with torch.no_grad():
-                ema_decay = min(1 - 1 / (i_iter - len_loader * sup_only_epoch + 1), cfg["net"]["ema_decay"])
-                t_params = [p.data for p in teacher.parameters()]
-                s_params = [p.data for p in model.parameters()]
-                if epoch == sup_only_epoch:
-                    # the reference re-binds t.data to a fresh tensor (:546-548); keep that un-aliasing
-                    new = torch._foreach_mul(t_params, ema_decay)
-                    torch._foreach_add_(new, s_params, alpha=1 - ema_decay)
-                    for p, n in zip(teacher.parameters(), new):
-                        p.data = n
-                else:
-                    torch._foreach_mul_(t_params, ema_decay)
-                    torch._foreach_add_(t_params, s_params, alpha=1 - ema_decay)
+        if epoch > sup_only_epoch and self.fused_opt is not None:
+            # SGD step and EMA (train_semi.py:531-548) in one multi-tensor kernel
+            ema_decay = min(1 - 1 / (i_iter - len_loader * sup_only_epoch + 1), cfg["net"]["ema_decay"])
+            self.fused_opt.step(ema_decay)
+        else:
+            self.optimizer.step()
+            if epoch >= sup_only_epoch:                                       # :531-548 EMA (parameters only)
+                with torch.no_grad():
+                    ema_decay = min(1 - 1 / (i_iter - len_loader * sup_only_epoch + 1), cfg["net"]["ema_decay"])
+                    t_params = [p.data for p in teacher.parameters()]
+                    s_params = [p.data for p in model.parameters()]
+                    if epoch == sup_only_epoch:
+                        # the reference re-binds t.data to a fresh tensor (:546-548); keep that un-aliasing
+                        new = torch._foreach_mul(t_params, ema_decay)
+                        torch._foreach_add_(new, s_params, alpha=1 - ema_decay)
+                        for p, n in zip(teacher.parameters(), new):
+                            p.data = n
+                    else:
+                        torch._foreach_mul_(t_params, ema_decay)
+                        torch._foreach_add_(t_params, s_params, alpha=1 - ema_decay)
 
         self._phase(ph, "optim_ema")
         losses = torch.stack([sup_loss.detach().float(), unsup_loss.detach().float(), contra_loss.detach().float()])
