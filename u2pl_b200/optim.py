@@ -62,7 +62,9 @@ class FusedSGDEMA:
         ch = np.asarray(chunks, dtype=np.uint32).reshape(-1)
         nbytes = table.size + ch.size * 4
         if self._pin is None or self._pin.numel() < nbytes:
-            self._pin = torch.empty(nbytes * 2, dtype=torch.uint8).pin_memory()
+            self._pin = torch.empty(nbytes * 2, dtype=torch.uint8)
+            if dev.type == "cuda":                            # (CPU tensors only ever reach here under the tests' emulated ABI)
+                self._pin = self._pin.pin_memory()
             self._dev = torch.empty(nbytes * 2, dtype=torch.uint8, device=dev)
         self._pin[:table.size].copy_(torch.from_numpy(table.copy()))
         self._pin[table.size:nbytes].copy_(torch.from_numpy(ch.view(np.uint8).copy()))
