@@ -392,12 +392,14 @@ int u2pl_peer_allreduce_f32(float *buf, int64_t n, void *const *peer_bases, int 
  * (~1.5k tiny launches).  tensor_table: DEVICE array of records of u2pl_sgd_tensor_bytes() (= 56) bytes each:
  *   { float *p; const float *g; float *m; float *t (or NULL); int64 n; float lr, wd; int32 first; int32 pad }
  * chunk_table: DEVICE array of n_chunks {uint32 tensor index, uint32 chunk index}; chunk = u2pl_sgd_chunk_elems() elements.
- *   d = g + wd*p;  m = first ? d : momentum*m + d;  p -= lr*m;  if do_ema and t: t = ema_decay*t + (1-ema_decay)*p
+ *   d = g + wd*p;  m = first ? d : momentum*m + d;  p -= lr*m;  if do_ema and t: t = ema_decay*t + ema_one_minus*p
+ * rounded where torch.optim.SGD (multi-tensor) and the reference's EMA expression round; ema_one_minus is the caller's
+ * float32(1 - decay) evaluated in double, as Python evaluates `(1 - ema_decay)` (train_semi.py:546) -- not 1.0f - ema_decay.
  * ---------------------------------------------------------------------- */
 int64_t u2pl_sgd_tensor_bytes(void);
 int64_t u2pl_sgd_chunk_elems(void);
 int u2pl_sgd_ema_step(const void *tensor_table, const void *chunk_table, int64_t n_chunks, float momentum, float ema_decay,
-                      int do_ema, void *stream);
+                      float ema_one_minus, int do_ema, void *stream);
 
 #ifdef __cplusplus
 }

@@ -368,7 +368,7 @@ class FakeLoss:
     def u2pl_sgd_chunk_elems(self):
         return 8192
 
-    def u2pl_sgd_ema_step(self, tensor_table, chunk_table, n_chunks, momentum, decay, do_ema, stream):
+    def u2pl_sgd_ema_step(self, tensor_table, chunk_table, n_chunks, momentum, decay, one_minus, do_ema, stream):
         import struct
         ch = _arr(chunk_table, 2 * n_chunks, ctypes.c_uint32).reshape(-1, 2)
         n_tensors = int(ch[:, 0].max()) + 1
@@ -383,7 +383,7 @@ class FakeLoss:
             p[:] = p - np.float32(lr) * m
             if do_ema and tp:
                 t = _arr(ctypes.c_void_p(tp), n, ctypes.c_float)
-                t[:] = np.float32(decay) * t + np.float32(1.0 - decay) * p
+                t[:] = np.float32(decay) * t + np.float32(one_minus) * p
         return 0
 
     def u2pl_ce_forward(self, logits, target, B, C, HW, ignore, nll, n_used, ws, ws_bytes, stream):

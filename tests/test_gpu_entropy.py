@@ -102,7 +102,13 @@ def _fused_vs_two_step(ops, x, target, percents, part_idx):
     assert torch.equal(thresh.view(torch.int32), thresh_f.view(torch.int32))    # NaN-safe bit comparison
     assert n_valid.item() == n_valid_f.item() and n_kept.item() == n_kept_f.item()
     assert torch.equal(t2, t_f) and torch.equal(mask, mask_f)
-    assert torch.equal(ent.view(torch.int32), ent_f.view(torch.int32))
+    # The entropy map is an internal quantity, exact (contract arithmetic) only inside each path's own candidate bands
+    # around the thresholds and hardware-approximate elsewhere; the bands of the two paths differ (22-bit
+    # bins vs 16-bit fine bins).  What both maps must agree on bit for bit is every comparison against every threshold.
+    assert (ent - ent_f).abs().max().item() <= 2.5e-5
+    for j in range(thresh.numel()):
+        if not torch.isnan(thresh[j]):
+            assert torch.equal(ent >= thresh[j], ent_f >= thresh[j]) and torch.equal(ent <= thresh[j], ent_f <= thresh[j])
     return ent_f, thresh_f, t_f, n_kept_f
 
 

@@ -47,15 +47,15 @@ def test_fused_sgd_ema_matches_torch():
                 for t, s in zip(my_t, my_p):
                     t.copy_(decay * t + (1 - decay) * s)
         for a, b in zip(ref_p, my_p):
-            assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), step
+            assert torch.allclose(a, b, rtol=2e-6, atol=5e-7), step
         for a, b in zip(ref_t, my_t):
-            assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), step
+            assert torch.allclose(a, b, rtol=2e-6, atol=5e-7), step
         for a, b in zip(ref_p, my_p):
-            assert torch.allclose(ref_opt.state[a]["momentum_buffer"], my_opt.state[b]["momentum_buffer"], rtol=2e-6, atol=1e-7)
+            assert torch.allclose(ref_opt.state[a]["momentum_buffer"], my_opt.state[b]["momentum_buffer"], rtol=2e-6, atol=5e-7)
     # torch's own step keeps working on the state the fused kernel maintained (checkpoint / fallback compatibility)
     for p, q, g in zip(ref_p, my_p, _make(999)):
         p.grad, q.grad = g.clone(), g.clone()
     ref_opt.step()
     my_opt.step()
     for a, b in zip(ref_p, my_p):
-        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7)
+        assert torch.allclose(a, b, rtol=2e-6, atol=5e-7)

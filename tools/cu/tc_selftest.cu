@@ -298,9 +298,9 @@ static uint16_t *dev_pattern(size_t n)
     return d;
 }
 
-static void perf(const Lib &L)
+static void perf(const Lib &L, int only)
 {
-    {   // stem max-pooling at the student batch: 32 x 257 x 257 x 128
+    if (only < 0) {   // stem max-pooling at the student batch: 32 x 257 x 257 x 128
         const int N = 32, H = 257, W = 257, C = 128, Ho = static_cast<int>(L.pool_out(H)), Wo = static_cast<int>(L.pool_out(W));
         const size_t nx = static_cast<size_t>(N) * H * W * C, ny = static_cast<size_t>(N) * Ho * Wo * C;
         uint16_t *x = dev_pattern(nx), *y = dev_pattern(ny), *dx = nullptr;
@@ -327,7 +327,9 @@ static void perf(const Lib &L)
                             {"layer3.conv3 1x1 256->1024", 16, 256, 65, 65, 1024, 1, 1}, {"layer4.conv2 3x3 d8 512->512", 16, 512, 65, 65, 512, 3, 8},
                             {"aspp 3x3 d12 2048->256", 16, 2048, 65, 65, 256, 3, 12}, {"head 3x3 1280->256", 16, 1280, 65, 65, 256, 3, 1},
                             {"decoder 3x3 256->256 @129", 16, 256, 129, 129, 256, 3, 1}, {"8192^3 as 1x1", 1, 8192, 8192, 1, 8192, 1, 1}};
+    int shape_i = -1;
     for (const Shape &sh : shapes) {
+        if (++shape_i != only && only >= 0) continue;
         const size_t nx = static_cast<size_t>(sh.N) * sh.H * sh.W * sh.Cin, ny = static_cast<size_t>(sh.N) * sh.H * sh.W * sh.Cout;
         const size_t nw = static_cast<size_t>(sh.Cout) * sh.k * sh.k * sh.Cin;
         uint16_t *x = dev_pattern(nx), *w = dev_pattern(nw), *y = dev_pattern(ny);
@@ -348,6 +350,12 @@ static void perf(const Lib &L)
         const double flop = 2.0 * sh.N * sh.H * sh.W * static_cast<double>(sh.Cout) * sh.Cin * sh.k * sh.k;
         const float t_conv = time_it([&] { L.conv(x, w, y, sh.N, sh.H, sh.W, sh.Cin, sh.Cout, sh.k, sh.d, sc, sf, nullptr, 1, nullptr); });
         printf("perf %-30s conv+bn+relu %8.3f ms %7.1f TFLOP/s", sh.name, t_conv, flop / t_conv / 1e9);
+        if (sh.k == 1 && sh.N > 1) {                   // bottleneck exit: + residual (read) in the epilogue
+            uint16_t *res = dev_pattern(ny);
+            const float t_res = time_it([&] { L.conv(x, w, y, sh.N, sh.H, sh.W, sh.Cin, sh.Cout, sh.k, sh.d, sc, sf, res, 1, nullptr); });
+            printf(" | +residual %8.3f ms (%.0f GB/s of x+res+y)", t_res, (nx + 2 * ny) * 2 / t_res / 1e6);
+            cudaFree(res);
+        }
         if (sh.k == 3) {
             const int64_t parts = L.parts(sh.N, sh.H, sh.W, sh.k);
             float *part = nullptr, *sums = nullptr, *wpart = nullptr;
@@ -395,6 +403,11 @@ int main(int argc, char **argv)
         fails += check_conv(L, 1, 64, 23, 17, 256, 3, 5, true, false);
         fails += check_conv(L, 1, 256, 30, 40, 512, 1, 1, true, false);
         fails += check_conv(L, 3, 192, 9, 40, 264, 3, 1, false, false);
+        // flat-tile kernel (conv_tc3.cu): tiles that straddle image boundaries, taps entirely outside the map, Cin % 64 != 0
+        // with several channel blocks, an M tail shorter than one epilogue warp's 32 rows
+        fails += check_conv(L, 3, 304, 13, 15, 256, 3, 12, true, false);
+        fails += check_conv(L, 2, 64, 33, 31, 48, 3, 1, true, false);
+        fails += check_conv(L, 5, 128, 9, 9, 1024, 1, 1, true, false);
     }
     if (all || !strcmp(what, "stats")) {
         fails += check_conv(L, 2, 64, 17, 19, 128, 3, 1, false, true);
@@ -417,7 +430,7 @@ int main(int argc, char **argv)
         fails += check_wgrad(L, 1, 264, 7, 17, 136, 2);
         fails += check_wgrad(L, 2, 512, 9, 20, 256, 12);                     // taps that fall entirely outside the map, 2 ci tiles
     }
-    if (!strcmp(what, "perf")) { perf(L); return 0; }
+    if (!strcmp(what, "perf")) { perf(L, argc > 2 ? atoi(argv[2]) : -1); return 0; }   // perf [shape index]
     printf("%s\n", fails ? "SELFTEST FAILED" : "SELFTEST PASSED");
     return fails ? 1 : 0;
 }

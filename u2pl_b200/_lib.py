@@ -71,7 +71,7 @@ SIGNATURES = {
     "u2pl_peer_allreduce_f32": (c_int, [_P, c_int64, POINTER(c_void_p), c_int, c_int, c_uint32, _S]),
     "u2pl_sgd_tensor_bytes": (c_int64, []),
     "u2pl_sgd_chunk_elems": (c_int64, []),
-    "u2pl_sgd_ema_step": (c_int, [_P, _P, c_int64, c_float, c_float, c_int, _S]),
+    "u2pl_sgd_ema_step": (c_int, [_P, _P, c_int64, c_float, c_float, c_float, c_int, _S]),
     "u2pl_bn_parts": (c_int64, []),
     "u2pl_bn_stats": (c_int, [_P, c_int64, c_int64, _P, _P, _S]),
     "u2pl_bn_finalize": (c_int, [_P, c_int64, c_double, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _S]),

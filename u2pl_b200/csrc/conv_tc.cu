@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "conv_tc2.cuh"
+#include "conv_tc3.cuh"
 
 namespace u2pl {
 
@@ -360,6 +361,14 @@ static void conv_run(unsigned grid, size_t smem, cudaStream_t st, const CUtensor
     conv_tc_kernel<kBN, kStats, kXform><<<grid, kXform ? convtc::kThreads + 128 : convtc::kThreads, smem, st>>>(mx, mw, p);
 }
 
+// Kernel selection: U2PL_CONV_V unset / 3 = flat-tile kernel (conv_tc3.cu) for everything but the operand-transform
+// variant; 1 = the patch-tiled 1-CTA kernel below for everything; 2 = the CTA-pair kernel where eligible.
+static bool flat_kernel(bool xform)
+{
+    static const int forced = [] { const char *e = getenv("U2PL_CONV_V"); return e ? atoi(e) : 0; }();
+    return !xform && forced != 1 && forced != 2;
+}
+
 static int conv_launch(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w, int64_t cin, int64_t cout,
                        int ksize, int dilation, const float *in_scale, const float *in_shift, int in_relu,
                        const float *scale, const float *shift, const void *residual, int relu,
@@ -373,8 +382,11 @@ static int conv_launch(const void *x, const void *wgt, void *out, int64_t n, int
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(out) |
          reinterpret_cast<uintptr_t>(residual)) & 15)
         return bad_arg("conv_bf16_nhwc: operands must be 16-byte aligned");
-    if (conv_tc2_eligible(cout, in_scale != nullptr || in_shift != nullptr || in_relu != 0))      // CTA-pair kernel (conv_tc2.cu)
+    const bool xform_req = in_scale != nullptr || in_shift != nullptr || in_relu != 0;
+    if (conv_tc2_eligible(cout, xform_req))           // CTA-pair kernel (conv_tc2.cu), opt-in
         return conv_tc2_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, scale, shift, residual, relu, stat_part, what, stream);
+    if (flat_kernel(xform_req))                       // default: flat pixel tiles, im2col TMA, TMA-store epilogue (conv_tc3.cu)
+        return conv_tc3_launch(x, wgt, out, n, h, w, cin, cout, ksize, dilation, scale, shift, residual, relu, stat_part, what, stream);
     ConvParams p;
     CUtensorMap mx, mw;
     bool ok;
@@ -452,12 +464,14 @@ static int64_t stat_parts_1cta(int64_t n, int64_t h, int64_t w, int ksize)
     return n * ((h + 7) / 8) * ((w + 15) / 16);
 }
 
-// rows of the caller's partial-sum buffer: the larger of the two kernels' needs (the pair kernel writes two per pixel tile)
+// rows of the caller's partial-sum buffer: the largest of the kernels' needs (the pair kernel writes two per pixel tile)
 extern "C" int64_t u2pl_conv_stat_parts(int64_t n, int64_t h, int64_t w, int ksize) { return conv_tc2_stat_parts(n, h, w, ksize); }
 
 static int stat_parts_used(int64_t n, int64_t h, int64_t w, int64_t cout, int ksize, bool xform)
 {
-    return static_cast<int>(conv_tc2_eligible(cout, xform) ? conv_tc2_stat_parts(n, h, w, ksize) : stat_parts_1cta(n, h, w, ksize));
+    if (conv_tc2_eligible(cout, xform)) return static_cast<int>(conv_tc2_stat_parts(n, h, w, ksize));
+    if (flat_kernel(xform)) return static_cast<int>(conv_tc3_stat_parts(n, h, w));
+    return static_cast<int>(stat_parts_1cta(n, h, w, ksize));
 }
 
 extern "C" int u2pl_conv_bf16_nhwc_stats(const void *x, const void *wgt, void *out, int64_t n, int64_t h, int64_t w,

@@ -365,8 +365,11 @@ static bool make_map_weight(CUtensorMap *map, const void *base, int64_t cout, in
 
 bool conv_tc2_eligible(int64_t cout, bool xform)
 {
+    // Opt-in (U2PL_CONV_V=2).  Measured on B200 (profiles/r02_conv_selftest_perf_*.txt): the pair kernel is correct but
+    // runs at ~0.55 PFLOP/s where the 1-CTA kernel reaches 1.05-1.2 PFLOP/s on the same layers, so the 1-CTA kernel is
+    // the default until the pair pipeline's stall is found.
     static const int forced = [] { const char *e = getenv("U2PL_CONV_V"); return e ? atoi(e) : 0; }();
-    if (forced == 1) return false;
+    if (forced != 2) return false;
     return !xform && cout > 128;
 }
 

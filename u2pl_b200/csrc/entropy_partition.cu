@@ -619,7 +619,7 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
 {
     __shared__ uint32_t s_pix[kCandTile];                 // candidates of the current tile: pixel index ...
     __shared__ uint8_t s_hit[kCandTile];                  // ... and the bands it falls into
-    __shared__ uint32_t s_cnt, warp_tot[8], s_pre22[kMaxT], s_below[kMaxT], s_band[kMaxT];
+    __shared__ uint32_t s_cnt, warp_tot[8], s_pre22[kMaxT], s_below[kMaxT], s_band[kMaxT], s_bcnt[kMaxT], s_bbase[kMaxT], s_bpos[kMaxT];
     __shared__ float s_lo[kMaxT], s_hi[kMaxT];
     __shared__ int s_nband;
     const uint32_t n_all = st->n;
@@ -716,8 +716,11 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
             }
         }
         __syncthreads();
-        // ---- phase 2: exact (contract) entropy of the candidates, one per thread
+        // ---- phase 2: exact (contract) entropy of the candidates, one per thread; the tile reserves its range of every
+        // band's list with ONE global atomic (an atomic per candidate put ~1e5 same-address operations through L2: 40 us)
         const uint32_t nc = s_cnt;
+        if (tid < kMaxT) { s_bcnt[tid] = 0; s_bpos[tid] = 0; }
+        __syncthreads();
         for (uint32_t j = tid; j < nc; j += 256) {
             const uint32_t i = s_pix[j];
             uint32_t hit = s_hit[j];
@@ -728,12 +731,23 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
             for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
             const float e = entropy_of<C>(v);
             ent[i] = e;
-            const uint32_t ek = float_key(e);
+            s_pix[j] = float_key(e);                       // the pixel index is no longer needed: keep the exact key instead
             while (hit) {
                 const int u = __ffs(hit) - 1;
                 hit &= hit - 1;
-                const uint32_t pos = atomicAdd(&st->cnt[u], 1u);
-                lists[static_cast<size_t>(u) * N + pos] = ek;
+                atomicAdd(&s_bcnt[u], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid < kMaxT && s_bcnt[tid]) s_bbase[tid] = atomicAdd(&st->cnt[tid], s_bcnt[tid]);
+        __syncthreads();
+        for (uint32_t j = tid; j < nc; j += 256) {
+            uint32_t hit = s_hit[j];
+            const uint32_t ek = s_pix[j];
+            while (hit) {
+                const int u = __ffs(hit) - 1;
+                hit &= hit - 1;
+                lists[static_cast<size_t>(u) * N + s_bbase[u] + atomicAdd(&s_bpos[u], 1u)] = ek;
             }
         }
         __syncthreads();
@@ -768,19 +782,26 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
 //   P4  numpy lerp -> thresholds (every CTA, redundantly; CTA 0 publishes) and the partition of the slice from shared
 //       memory: target_out = (entropy >= thresh[part_idx] && valid) ? ignore : class, drop mask, kept count
 // Three grid barriers replace four launches + three scans.  Soundness argument: see the two-level path (kDelta).
-constexpr int kChainThreads = 1024;
-constexpr int kChainMaxSlice = 32768;                     // pixels per CTA: 128 KB of keys + 32 KB of class ids
-constexpr uint32_t kFineBase = 0x8000u + (103u << 7);     // key >> 16 of 2^-24
-constexpr int kFineBins = ((129 - 103) << 7) + 2;         // [2^-24, 4) at 128 bins per octave, + one clamp bin on either side
-constexpr uint32_t kCandCap = 16384;                      // candidates compacted per round (16-bit index + band mask)
+constexpr int kChainThreads = 768;                        // two CTAs per SM: 1536 threads keep ~40 registers each, like entropy_fast_hist
+constexpr int kChainCtasPerSm = 2;
+constexpr int kChainMaxSlice = 16384;                     // pixels per CTA: 64 KB of keys + 16 KB of class ids
+// Fine histogram: LINEAR in the entropy value, 1024 bins per unit over [0, 4) (an entropy is at most ln C < 4 for
+// C <= 54; the last bin is open-ended).  The error bound kDelta of the fast evaluation is absolute, so is the bin width:
+// a band (bin + 3 kDelta either side) is ~1.6e-3 wide and holds a few thousand of the 4.2 M pixels, where 128 bins per
+// OCTAVE made bands of 0.016 around the 90th percentile and ~1e5 candidates.
+constexpr int kFineBins = 4096;
+constexpr float kFineScale = 1024.0f;
+constexpr int kFinePad = 4608;                            // histogram words: kChainThreads x 6 bins per thread in the scan
+constexpr uint32_t kCandCap = 4096;                       // candidates compacted per round (16-bit index + band mask)
+constexpr int kSelBins = 2048;                            // P3 radix digit: 11 bits
 
-__device__ __forceinline__ uint32_t fine_bin(uint32_t key)
+// monotone in h: bin b holds [b/1024, (b+1)/1024); bin 0 also takes everything below 0, the last bin everything above
+__device__ __forceinline__ uint32_t fine_bin(float h)
 {
-    const uint32_t hi = key >> 16;
-    return hi < kFineBase ? 0u : min(hi - kFineBase + 1u, static_cast<uint32_t>(kFineBins - 1));
+    const float x = h * kFineScale;                        // exact (power of two)
+    return x < 1.0f ? 0u : min(static_cast<uint32_t>(x), static_cast<uint32_t>(kFineBins - 1));
 }
-// keys of bin b are [fine_lo_key(b), fine_lo_key(b+1)); bin 0 starts at key 0, the last bin never ends
-__device__ __forceinline__ uint32_t fine_lo_key(uint32_t b) { return b == 0 ? 0u : (kFineBase + b - 1u) << 16; }
+__device__ __forceinline__ float fine_lo(uint32_t b) { return static_cast<float>(b) * (1.0f / kFineScale); }
 
 __device__ __forceinline__ void phase_stamp(SelState *st, int k)
 {
@@ -804,8 +825,8 @@ __device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t goal)
     __syncthreads();
 }
 
-// block-wide exclusive scan position of `cnt` (one value per thread, 1024 threads)
-__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t cnt, uint32_t *warp_tot)
+// block-wide exclusive scan position of `cnt` (one value per thread); warp_tot: one word per warp
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t cnt, uint32_t *warp_tot)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t inc = cnt;
@@ -822,37 +843,60 @@ __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t cnt, uint32_t 
     return base + inc - cnt;
 }
 
+// P1  fast entropy of the slice (coalesced, C loads in flight per thread) -> ent[], s_keys[], s_cls[] and a FINE histogram:
+//     the top 16 key bits (sign, exponent, 7 mantissa bits = 128 bins per octave) restricted to the range an entropy can
+//     take, [2^-24, 4) -> 3328 bins + two clamp bins.
+// P2  every CTA (redundantly) selects the bin of each target rank from the merged histogram -- which also tells how many
+//     valid pixels lie in LOWER bins, so nothing has to be counted per pixel; a target's candidate band is its bin widened
+//     by 3*kDelta; band test on s_keys; the candidates of the slice are compacted and re-evaluated AT ONCE under the
+//     arithmetic contract (exact value back into ent[] and s_keys[]); the CTA reserves its range of each band's global
+//     list with ONE atomic per band (one atomic per candidate serialised ~1e5 same-address atomics in L2: 40 us)
+// P3  CTA t mod G: exact select of target t inside its candidate list -- min/max first, then 11-bit radix digits over the
+//     bits in which the candidates actually differ (they share their leading ~15 bits; a digit they all share would put
+//     every shared-memory atomic on one address)
+// P4  numpy lerp -> thresholds (every CTA, redundantly; CTA 0 publishes) and the partition of the slice from shared
+//     memory: target_out = (entropy >= thresh[part_idx] && valid) ? ignore : class, drop mask, kept count
+// Three grid barriers replace four launches + three scans.  Soundness argument: see the two-level path (kDelta).
 template <int C>
-__global__ void __launch_bounds__(kChainThreads, 1)
+__global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm)
 entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict__ target_in, uint32_t HW, uint32_t N,
-                     uint32_t slice, int64_t ignore, Percents pc, int nq, int part_idx,
+                     uint32_t slice, int64_t ignore, Percents pc, int nq, int part_idx, int dbg,
                      float *__restrict__ ent, float *__restrict__ thresh, int64_t *__restrict__ n_valid,
                      int64_t *__restrict__ target_out, uint8_t *__restrict__ drop_mask, unsigned long long *__restrict__ n_kept,
                      uint32_t *__restrict__ hist, SelState *__restrict__ st, uint32_t *__restrict__ lists)
 {
     extern __shared__ uint32_t chain_smem[];
     uint32_t *s_keys = chain_smem;                         // [slice]
-    uint32_t *s_hist = s_keys + slice;                     // [kFineBins rounded to 4096]: fine histogram; later select histogram
-    uint16_t *s_pix = reinterpret_cast<uint16_t *>(s_hist + 4096);       // [kCandCap] candidate slice-local index
-    uint8_t *s_hit = reinterpret_cast<uint8_t *>(s_pix + kCandCap);      // [kCandCap] candidate band mask
+    uint32_t *s_hist = s_keys + slice;                     // [kFinePad]: fine histogram; later the select histogram
+    uint16_t *s_pix = reinterpret_cast<uint16_t *>(s_hist + kFinePad);   // [kCandCap] candidate slice-local index
+    uint8_t *s_hit = reinterpret_cast<uint8_t *>(s_pix + kCandCap);      // [kCandCap] candidate band mask (kMaxT <= 8 bands)
     uint8_t *s_cls = s_hit + kCandCap;                     // [slice] class id of the pixel (255 stands for every ignored one)
-    __shared__ uint32_t warp_tot[32], s_grank[kMaxT], s_tbin[kMaxT], s_band[kMaxT], s_below[kMaxT];
-    __shared__ float s_gamma[kMaxQ], s_lo[kMaxT], s_hi[kMaxT], s_thr[kMaxQ];
-    __shared__ uint32_t s_n, s_cnt, s_sel_prefix, s_sel_rank, s_wide;
+    __shared__ uint32_t warp_tot[32], s_grank[kMaxT], s_tbin[kMaxT], s_tcum[kMaxT], s_band[kMaxT];
+    __shared__ uint32_t s_bcum[kMaxT], s_bcnt[kMaxT], s_blow[kMaxT], s_bbase[kMaxT], s_bpos[kMaxT];
+    __shared__ float s_gamma[kMaxQ], s_lo[kMaxT], s_hi[kMaxT], s_binlo[kMaxT], s_thr[kMaxQ];
+    __shared__ uint32_t s_n, s_cnt, s_sel_prefix, s_sel_rank, s_wide, s_kmin, s_kmax;
     __shared__ int s_nband;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = 2 * nq;
     const uint32_t G = gridDim.x;
-    const uint32_t base = blockIdx.x * slice;
-    const uint32_t cnt = (base < N) ? min(slice, N - base) : 0u;
+    // CTA b owns the pixel blocks b, b + G, b + 2G, ... of kChainThreads pixels each (all CTAs sweep the same region of
+    // every class plane at the same time, like a grid-stride kernel: contiguous per-CTA slices made 21 x 296 separate
+    // DRAM streams and cost a third of the bandwidth).  Slice-local index j = k * kChainThreads + tid.
+    const uint32_t nblk = slice / kChainThreads;           // blocks per CTA (slice is a multiple of kChainThreads)
+    const uint32_t cnt = slice;                            // local indices scanned by the later phases; pixels beyond N hold kInvalidKey
+    auto global_of = [&](uint32_t j) { return ((j / kChainThreads) * G + blockIdx.x) * kChainThreads + (j % kChainThreads); };
 
     // ---------------------------------------------------------------- P1
     phase_stamp(st, 0);
-    for (int j = tid; j < 4096; j += kChainThreads) s_hist[j] = 0;
+    unsigned long long *dbg_t = reinterpret_cast<unsigned long long *>(hist + 5120) + blockIdx.x * 2;   // (U2PL_CHAIN_TIMING) free words of hist2
+    if (dbg && tid == 0) { unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); dbg_t[0] = t0; }
+    for (int j = tid; j < kFinePad; j += kChainThreads) s_hist[j] = 0;
     if (tid == 0) s_wide = 0;
     __syncthreads();
-    for (uint32_t j = tid; j < cnt; j += kChainThreads) {
-        const uint32_t i = base + j;
+    for (uint32_t k = 0; k < nblk; ++k) {
+        const uint32_t j = k * kChainThreads + tid;
+        const uint32_t i = (k * G + blockIdx.x) * kChainThreads + tid;
+        if (i >= N) { s_keys[j] = kInvalidKey; s_cls[j] = 255; continue; }
         const uint32_t b = i / HW, p = i - b * HW;
         const float *x = logits + static_cast<size_t>(b) * C * HW + p;
         float v[C];
@@ -866,21 +910,22 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
         s_keys[j] = key;
         s_cls[j] = valid ? static_cast<uint8_t>(t) : static_cast<uint8_t>(255);
         if (valid && (t < 0 || t > 254)) s_wide = 1;       // a label that one byte cannot hold: P4 re-reads target_in
-        if (valid) hist_add(s_hist, fine_bin(key));
+        if (valid && !(dbg & 2)) hist_add(s_hist, fine_bin(h));
     }
     __syncthreads();
     for (int j = tid; j < kFineBins; j += kChainThreads)
         if (s_hist[j]) atomicAdd(&hist[j], s_hist[j]);
     phase_stamp(st, 1);
+    if (dbg && tid == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); dbg_t[1] = t1; }
     grid_barrier(&st->bar, G);
     phase_stamp(st, 2);
 
     // ---------------------------------------------------------------- P2: bins of the target ranks, bands, candidates
     {
-        const uint4 q = (tid * 4 < 4096) ? __ldcg(reinterpret_cast<const uint4 *>(hist) + tid) : make_uint4(0, 0, 0, 0);
-        const uint32_t loc[4] = {q.x, q.y, q.z, q.w};      // thread t owns bins 4t..4t+3 (the global array is padded to 4096)
-        const uint32_t sum = loc[0] + loc[1] + loc[2] + loc[3];
-        const uint32_t excl = block_excl_scan_1024(sum, warp_tot);
+        uint32_t loc[6], sum = 0;                          // thread t owns bins 6t..6t+5 (the global array is padded to kFinePad)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { loc[k] = __ldcg(hist + tid * 6 + k); sum += loc[k]; }
+        const uint32_t excl = block_excl_scan(sum, warp_tot);
         if (tid == kChainThreads - 1) s_n = excl + sum;
         __syncthreads();
         const uint32_t n = s_n;
@@ -906,9 +951,9 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                 if (r >= excl && r < excl + sum) {
                     uint32_t cum = excl;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (r < cum + loc[j]) { s_tbin[t] = tid * 4 + j; break; }
-                        cum += loc[j];
+                    for (int k = 0; k < 6; ++k) {
+                        if (r < cum + loc[k]) { s_tbin[t] = tid * 6 + k; s_tcum[t] = cum; break; }
+                        cum += loc[k];
                     }
                 }
             }
@@ -925,8 +970,10 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                 if (b < 0) {
                     b = nb++;
                     const uint32_t bin = s_tbin[t];
-                    s_lo[b] = (bin == 0) ? __uint_as_float(0xff800000u) : key_float(fine_lo_key(bin)) - 3.0f * kDelta;
-                    s_hi[b] = (bin == kFineBins - 1) ? __uint_as_float(0x7f800000u) : key_float(fine_lo_key(bin + 1)) + 3.0f * kDelta;
+                    s_binlo[b] = (bin == 0) ? __uint_as_float(0xff800000u) : fine_lo(bin);
+                    s_lo[b] = (bin == 0) ? __uint_as_float(0xff800000u) : fine_lo(bin) - 3.0f * kDelta;
+                    s_hi[b] = (bin == kFineBins - 1) ? __uint_as_float(0x7f800000u) : fine_lo(bin + 1) + 3.0f * kDelta;
+                    s_bcum[b] = s_tcum[t];                 // valid pixels in lower bins: fast value < s_binlo[b]
                 }
                 s_band[t] = static_cast<uint32_t>(b);
             }
@@ -937,84 +984,37 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                 for (int j = 0; j < nq; ++j) st->gamma[j] = s_gamma[j];
             }
         }
-        if (tid < kMaxT) s_below[tid] = 0;
         __syncthreads();
         const int U = s_nband;
-        float lo[kMaxT], hi[kMaxT];
-        uint32_t below[kMaxT];
-#pragma unroll
-        for (int u = 0; u < kMaxT; ++u) {
-            below[u] = 0;
-            lo[u] = (u < U) ? s_lo[u] : __uint_as_float(0x7f800000u);     // +inf: nothing is inside, everything "below" (unused)
-            hi[u] = (u < U) ? s_hi[u] : lo[u];
-        }
         // Candidates are compacted (16-bit slice-local index + band mask) and then re-evaluated all at once, one per
         // thread, so the ~3 us latency of an exact evaluation (C strided loads + ~900 dependent issue slots) is paid once.
         // A slice holding more than kCandCap candidates (massive ties) is processed in several rounds of kCandCap keys.
+        bool bounded = false;
         for (uint32_t tb = 0; tb < cnt; ) {
             __syncthreads();
             if (tid == 0) s_cnt = 0;
+            if (tid < kMaxT) { s_bcnt[tid] = 0; s_blow[tid] = 0; s_bpos[tid] = 0; }
             __syncthreads();
-            // a round covers as many keys as can never overflow the staging area: everything when the slice is small,
-            // else kCandCap keys (the common case has a few hundred candidates; one round = the whole slice is attempted
-            // first and kept if it fits)
-            const bool whole = (tb == 0);
-            const uint32_t te = whole ? cnt : min(cnt, tb + kCandCap);
-            uint32_t below_r[kMaxT];
-#pragma unroll
-            for (int u = 0; u < kMaxT; ++u) below_r[u] = 0;
+            const uint32_t te = bounded ? min(cnt, tb + kCandCap) : cnt;
             for (uint32_t j = tb + tid; j < te; j += kChainThreads) {
                 const uint32_t k = s_keys[j];
                 if (k == kInvalidKey) continue;
                 const float h = key_float(k);
                 uint32_t hit = 0;
-#pragma unroll
-                for (int u = 0; u < kMaxT; ++u) {
-                    below_r[u] += (u < U && h < lo[u]) ? 1u : 0u;
-                    hit |= (u < U && h >= lo[u] && h < hi[u]) ? (1u << u) : 0u;
-                }
+                for (int u = 0; u < U; ++u) hit |= (h >= s_lo[u] && h < s_hi[u]) ? (1u << u) : 0u;
                 if (hit) {
                     const uint32_t pos = atomicAdd(&s_cnt, 1u);
                     if (pos < kCandCap) { s_pix[pos] = static_cast<uint16_t>(j); s_hit[pos] = static_cast<uint8_t>(hit); }
                 }
             }
             __syncthreads();
-            uint32_t nc = s_cnt;
-            if (whole && nc > kCandCap) {                  // did not fit: redo this stretch in bounded rounds
-                __syncthreads();
-                if (tid == 0) s_cnt = 0;
-                __syncthreads();
-                const uint32_t te2 = min(cnt, tb + kCandCap);
-#pragma unroll
-                for (int u = 0; u < kMaxT; ++u) below_r[u] = 0;
-                for (uint32_t j = tb + tid; j < te2; j += kChainThreads) {
-                    const uint32_t k = s_keys[j];
-                    if (k == kInvalidKey) continue;
-                    const float h = key_float(k);
-                    uint32_t hit = 0;
-#pragma unroll
-                    for (int u = 0; u < kMaxT; ++u) {
-                        below_r[u] += (u < U && h < lo[u]) ? 1u : 0u;
-                        hit |= (u < U && h >= lo[u] && h < hi[u]) ? (1u << u) : 0u;
-                    }
-                    if (hit) {
-                        const uint32_t pos = atomicAdd(&s_cnt, 1u);
-                        s_pix[pos] = static_cast<uint16_t>(j);
-                        s_hit[pos] = static_cast<uint8_t>(hit);
-                    }
-                }
-                __syncthreads();
-                nc = s_cnt;
-                tb = te2;
-            } else {
-                tb = te;
-            }
-#pragma unroll
-            for (int u = 0; u < kMaxT; ++u) below[u] += below_r[u];
+            const uint32_t nc = s_cnt;
+            if (nc > kCandCap) { bounded = true; continue; }   // did not fit (only possible for the whole-slice attempt): redo in bounded rounds
             for (uint32_t c2 = tid; c2 < nc; c2 += kChainThreads) {       // exact (contract) entropy of the candidates
                 const uint32_t j = s_pix[c2];
                 uint32_t hit = s_hit[c2];
-                const uint32_t i = base + j;
+                const float hfast = key_float(s_keys[j]);
+                const uint32_t i = global_of(j);
                 const uint32_t b = i / HW, p = i - b * HW;
                 const float *x = logits + static_cast<size_t>(b) * C * HW + p;
                 float v[C];
@@ -1022,64 +1022,103 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                 for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
                 const float e = entropy_of<C>(v);
                 ent[i] = e;
-                const uint32_t ek = float_key(e);
-                s_keys[j] = ek;
+                s_keys[j] = float_key(e);
                 while (hit) {
                     const int u = __ffs(hit) - 1;
                     hit &= hit - 1;
-                    const uint32_t pos = atomicAdd(&st->cnt[u], 1u);
-                    lists[static_cast<size_t>(u) * N + pos] = ek;
+                    atomicAdd(&s_bcnt[u], 1u);
+                    if (hfast < s_binlo[u]) atomicAdd(&s_blow[u], 1u);     // counted in s_bcum although it is a candidate
                 }
             }
+            __syncthreads();
+            if (tid < U && s_bcnt[tid]) {                  // ONE global atomic per band per CTA reserves the list range
+                s_bbase[tid] = atomicAdd(&st->cnt[tid], s_bcnt[tid]);
+                if (s_blow[tid]) atomicAdd(&st->below[tid], s_blow[tid]);
+            }
+            __syncthreads();
+            for (uint32_t c2 = tid; c2 < nc; c2 += kChainThreads) {
+                const uint32_t j = s_pix[c2];
+                uint32_t hit = s_hit[c2];
+                const uint32_t ek = s_keys[j];
+                while (hit) {
+                    const int u = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    lists[static_cast<size_t>(u) * N + s_bbase[u] + atomicAdd(&s_bpos[u], 1u)] = ek;
+                }
+            }
+            tb = te;
         }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < kMaxT; ++u) {
-            const uint32_t sm = static_cast<uint32_t>(warp_sum_i(static_cast<int>(below[u])));
-            if (lane == 0 && sm) atomicAdd(&s_below[u], sm);
-        }
-        __syncthreads();
-        if (tid < U && s_below[tid]) atomicAdd(&st->below[tid], s_below[tid]);
     }
     grid_barrier(&st->bar, 2 * G);
     phase_stamp(st, 3);
 
     // ---------------------------------------------------------------- P3: exact select, target t on CTA t mod G
     for (int t = blockIdx.x; n_all != 0 && t < T; t += static_cast<int>(G)) {       // (grids smaller than T loop)
-        uint32_t *sel = s_hist;                            // [2048]
+        uint32_t *sel = s_hist;                            // [kSelBins]
         __syncthreads();
         const uint32_t u = s_band[t];
         const uint32_t n = __ldcg(&st->cnt[u]);
-        const uint32_t r0 = s_grank[t] - __ldcg(&st->below[u]);           // unsigned: a violated invariant shows as r0 >= n
+        // rank among the candidates: pixels surely below = those in lower bins that are not candidates themselves
+        const uint32_t r0 = s_grank[t] - (s_bcum[u] - __ldcg(&st->below[u]));      // unsigned: a violated invariant shows as r0 >= n
         const uint32_t *list = lists + static_cast<size_t>(u) * N;
         if (r0 >= n) {
             if (tid == 0) st->val[t] = __uint_as_float(0x7fc00000u);
-        } else {
-            if (tid == 0) { s_sel_prefix = 0; s_sel_rank = r0; }
-            const int shifts[3] = {21, 10, 0}, nbits[3] = {11, 11, 10};
-            for (int pass = 0; pass < 3; ++pass) {
-                sel[tid] = 0; sel[tid + 1024] = 0;
-                __syncthreads();
-                const uint32_t pre = s_sel_prefix, r = s_sel_rank;
-                const int sh = shifts[pass], hb = sh + nbits[pass];
-                const uint32_t mask = (1u << nbits[pass]) - 1u;
-                for (uint32_t j = tid; j < n; j += kChainThreads) {
-                    const uint32_t k = __ldcg(list + j);
-                    if (pass == 0 || (k >> hb) == pre) atomicAdd(&sel[(k >> sh) & mask], 1u);
-                }
-                __syncthreads();
-                const uint32_t c0 = sel[2 * tid], c1 = sel[2 * tid + 1], sum = c0 + c1;
-                const uint32_t excl = block_excl_scan_1024(sum, warp_tot);
-                __syncthreads();
-                if (r >= excl && r < excl + sum) {
-                    const uint32_t bin = (r < excl + c0) ? 2 * tid : 2 * tid + 1;
-                    s_sel_prefix = (pre << nbits[pass]) | bin;
-                    s_sel_rank = r - ((r < excl + c0) ? excl : excl + c0);
-                }
-                __syncthreads();
-            }
-            if (tid == 0) st->val[t] = key_float(s_sel_prefix);
+            continue;
         }
+        uint32_t kmin = 0xffffffffu, kmax = 0u;
+        for (uint32_t j0 = tid; j0 < n; j0 += 4 * kChainThreads) {       // four independent L2 loads in flight per thread
+            uint32_t kk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) kk[e] = (j0 + e * kChainThreads < n) ? __ldcg(list + j0 + e * kChainThreads) : __ldcg(list + tid % n);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { kmin = min(kmin, kk[e]); kmax = max(kmax, kk[e]); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        }
+        if (tid == 0) { s_kmin = 0xffffffffu; s_kmax = 0u; s_sel_prefix = 0; s_sel_rank = r0; }
+        __syncthreads();
+        if (lane == 0) { atomicMin(&s_kmin, kmin); atomicMax(&s_kmax, kmax); }
+        __syncthreads();
+        const uint32_t diff = s_kmin ^ s_kmax;
+        const int nb = diff ? 32 - __clz(diff) : 0;        // the candidates agree on their leading 32 - nb bits
+        const uint32_t low_mask = (nb == 32) ? 0xffffffffu : ((1u << nb) - 1u);
+        for (int done = 0; done < nb; ) {
+            const int w = min(11, nb - done), sh = nb - done - w;
+            for (int j = tid; j < kSelBins; j += kChainThreads) sel[j] = 0;
+            __syncthreads();
+            const uint32_t pre = s_sel_prefix, r = s_sel_rank;
+            const uint32_t dmask = (1u << w) - 1u;
+            for (uint32_t j0 = tid; j0 < n; j0 += 4 * kChainThreads) {
+                uint32_t kk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) kk[e] = (j0 + e * kChainThreads < n) ? __ldcg(list + j0 + e * kChainThreads) : 0u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t k = kk[e] & low_mask;
+                    if (j0 + e * kChainThreads < n && (done == 0 || (k >> (sh + w)) == pre)) hist_add(sel, (k >> sh) & dmask);
+                }
+            }
+            __syncthreads();
+            uint32_t loc[3], sum = 0;                      // thread t owns bins 3t..3t+2 (768 x 3 >= 2048)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { loc[k] = (tid * 3 + k < kSelBins) ? sel[tid * 3 + k] : 0u; sum += loc[k]; }
+            const uint32_t excl = block_excl_scan(sum, warp_tot);
+            __syncthreads();
+            if (r >= excl && r < excl + sum) {
+                uint32_t cum = excl;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (r >= cum && r < cum + loc[k]) { s_sel_prefix = (pre << w) | static_cast<uint32_t>(tid * 3 + k); s_sel_rank = r - cum; }
+                    cum += loc[k];
+                }
+            }
+            __syncthreads();
+            done += w;
+        }
+        if (tid == 0) st->val[t] = key_float((s_kmin & ~low_mask) | s_sel_prefix);
     }
     grid_barrier(&st->bar, 3 * G);
     phase_stamp(st, 4);
@@ -1104,8 +1143,10 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
         const float th = s_thr[part_idx];
         const bool wide = s_wide != 0;
         int kept = 0;
-        for (uint32_t j = tid; j < cnt; j += kChainThreads) {
-            const uint32_t i = base + j;
+        for (uint32_t k = 0; k < nblk; ++k) {
+            const uint32_t j = k * kChainThreads + tid;
+            const uint32_t i = (k * G + blockIdx.x) * kChainThreads + tid;
+            if (i >= N) continue;
             const uint32_t key = s_keys[j];
             const bool valid = (key != kInvalidKey);
             const bool drop = valid && (key_float(key) >= th);
@@ -1402,11 +1443,13 @@ static int launch_chain(const float *logits, const int64_t *target_in, uint32_t 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     if (!coop) return 0;
-    uint32_t grid = static_cast<uint32_t>(std::min<long long>(sms, std::max<long long>(1, (static_cast<long long>(N) + 4095) / 4096)));
-    uint32_t slice = (N + grid - 1) / grid;
-    slice = (slice + 3u) & ~3u;
+    uint32_t grid = static_cast<uint32_t>(std::min<long long>(static_cast<long long>(kChainCtasPerSm) * sms,
+                                                               std::max<long long>(1, (static_cast<long long>(N) + 4095) / 4096)));
+    const uint32_t blocks = (N + kChainThreads - 1) / kChainThreads;       // pixel blocks, dealt round-robin to the CTAs
+    if (grid > blocks) grid = blocks;
+    uint32_t slice = ((blocks + grid - 1) / grid) * kChainThreads;
     if (slice > static_cast<uint32_t>(kChainMaxSlice)) return 0;
-    auto smem_for = [](size_t sl) { return sl * 4 + 4096 * 4 + kCandCap * 3 + sl; };
+    auto smem_for = [](size_t sl) { return sl * 4 + kFinePad * 4 + kCandCap * 3 + sl; };
     const size_t smem = smem_for(slice);
     static bool configured = false;
     if (!configured) {
@@ -1421,7 +1464,9 @@ static int launch_chain(const float *logits, const int64_t *target_in, uint32_t 
     Percents pcc = pc;
     unsigned long long *nk = reinterpret_cast<unsigned long long *>(n_kept);
     uint32_t hw_ = hw, N_ = N;
-    void *args[] = {&logits, &target_in, &hw_, &N_, &slice, &ignore, &pcc, &nq, &part_idx, &entropy, &thresh, &n_valid,
+    static const int dbg = [] { const char *e = getenv("U2PL_CHAIN_TIMING"); return e ? atoi(e) : 0; }();
+    int dbg_ = dbg;
+    void *args[] = {&logits, &target_in, &hw_, &N_, &slice, &ignore, &pcc, &nq, &part_idx, &dbg_, &entropy, &thresh, &n_valid,
                     &target_out, &drop_mask, &nk, const_cast<uint32_t **>(&w.hist1),      // hist1: 4096 words, zeroed: the fine histogram
                     const_cast<SelState **>(&w.st), &lists};
     cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(entropy_chain_kernel<C>), dim3(grid), dim3(kChainThreads),
@@ -1436,6 +1481,17 @@ static int launch_chain(const float *logits, const int64_t *target_in, uint32_t 
         fprintf(stderr, "[entropy_chain] grid %u slice %u | P1 %.1f us | bar1 %.1f | P2+bar2 %.1f | P3+bar3 %.1f | P4 %.1f | total %.1f us (CTA 0)\n",
                 grid, slice, (h.stamp[1] - h.stamp[0]) * 1e-3, (h.stamp[2] - h.stamp[1]) * 1e-3, (h.stamp[3] - h.stamp[2]) * 1e-3,
                 (h.stamp[4] - h.stamp[3]) * 1e-3, (h.stamp[5] - h.stamp[4]) * 1e-3, (h.stamp[5] - h.stamp[0]) * 1e-3);
+        static unsigned long long tt[2 * 1024];
+        if (grid <= 1024) {
+            cudaMemcpy(tt, w.hist1 + 5120, grid * 16, cudaMemcpyDeviceToHost);
+            unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0; double dsum = 0, dmax = 0, dmin = 1e30;
+            for (uint32_t b = 0; b < grid; ++b) {
+                s0 = std::min(s0, tt[2 * b]); s1 = std::max(s1, tt[2 * b]); e0 = std::min(e0, tt[2 * b + 1]); e1 = std::max(e1, tt[2 * b + 1]);
+                const double d = (tt[2 * b + 1] - tt[2 * b]) * 1e-3; dsum += d; dmax = std::max(dmax, d); dmin = std::min(dmin, d);
+            }
+            fprintf(stderr, "[entropy_chain] P1 per CTA: start spread %.1f us, end spread %.1f us (first end %.1f, last end %.1f after first start), duration min %.1f avg %.1f max %.1f us\n",
+                    (s1 - s0) * 1e-3, (e1 - e0) * 1e-3, (e0 - s0) * 1e-3, (e1 - s0) * 1e-3, dmin, dsum / grid, dmax);
+        }
     }
     return check_launch("entropy_chain");
 }

@@ -7,7 +7,7 @@
 //   per element  read  p, g, m, t   (16 B)   write  p, m, t   (12 B)            [m = momentum buffer]
 // The host passes a table of tensors (pointers, sizes, per-tensor lr / weight decay) and a table of chunks
 // (tensor index, element offset); block b processes chunk b.  Arithmetic order follows torch.optim.SGD:
-//   d = g + wd*p;  m = first ? d : momentum*m + d;  p = p - lr*m;  t = decay*t + (1-decay)*p.
+//   d = g + wd*p;  m = first ? d : momentum*m + d;  p = p - lr*m;  t = decay*t + (1-decay)*p  (rounded where torch rounds).
 #include "common.cuh"
 
 namespace u2pl {
@@ -23,7 +23,7 @@ struct SgdTensor {
 constexpr int kSgdChunk = 8192;                          // elements per block
 
 __global__ void __launch_bounds__(256)
-sgd_ema_kernel(const SgdTensor *__restrict__ tensors, const uint2 *__restrict__ chunks, float momentum, float decay, int do_ema)
+sgd_ema_kernel(const SgdTensor *__restrict__ tensors, const uint2 *__restrict__ chunks, float momentum, float decay, float one_minus, int do_ema)
 {
     const uint2 ch = chunks[blockIdx.x];
     const SgdTensor T = tensors[ch.x];
@@ -35,12 +35,13 @@ sgd_ema_kernel(const SgdTensor *__restrict__ tensors, const uint2 *__restrict__ 
     float *t = T.t ? T.t + off : nullptr;
     const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                        reinterpret_cast<uintptr_t>(t)) & 15) == 0;
-    const float one_minus = 1.0f - decay;
     auto upd = [&](float &pv, float gv, float &mv, float &tv) {
+        // rounding points of torch's multi-tensor SGD (_foreach_add(alpha) is an fma; _foreach_mul_ then _foreach_add_
+        // round twice) and of the reference's EMA expression `d * t + (1 - d) * s` (three roundings)
         const float d = fmaf(T.wd, pv, gv);
-        mv = T.first ? d : fmaf(momentum, mv, d);
+        mv = T.first ? d : __fadd_rn(__fmul_rn(momentum, mv), d);
         pv = fmaf(-T.lr, mv, pv);
-        if (do_ema) tv = fmaf(decay, tv, one_minus * pv);
+        if (do_ema) tv = __fadd_rn(__fmul_rn(decay, tv), __fmul_rn(one_minus, pv));
     };
     if (vec) {
         const int n4 = n >> 2;
@@ -78,10 +79,10 @@ extern "C" int64_t u2pl_sgd_tensor_bytes(void) { return static_cast<int64_t>(siz
 extern "C" int64_t u2pl_sgd_chunk_elems(void) { return kSgdChunk; }
 
 extern "C" int u2pl_sgd_ema_step(const void *tensor_table, const void *chunk_table, int64_t n_chunks, float momentum, float ema_decay,
-                                 int do_ema, void *stream)
+                                 float ema_one_minus, int do_ema, void *stream)
 {
     if (!tensor_table || !chunk_table || n_chunks <= 0 || n_chunks >= (1LL << 31)) return bad_arg("sgd_ema_step: empty or oversized tables");
     sgd_ema_kernel<<<static_cast<unsigned>(n_chunks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const SgdTensor *>(tensor_table), static_cast<const uint2 *>(chunk_table), momentum, ema_decay, do_ema);
+        static_cast<const SgdTensor *>(tensor_table), static_cast<const uint2 *>(chunk_table), momentum, ema_decay, ema_one_minus, do_ema);
     return check_launch("sgd_ema_step");
 }

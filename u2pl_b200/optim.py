@@ -11,6 +11,11 @@ from . import _lib
 from .ops import _p, _stream
 
 
+def _dense(t):
+    """Non-overlapping and dense: numel elements laid out without holes in some dimension order."""
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)) or t.numel() <= 1
+
+
 class FusedSGDEMA:
     def __init__(self, optimizer, student_params=None, teacher_params=None):
         assert isinstance(optimizer, torch.optim.SGD), "fused update is built for torch.optim.SGD (lr_helper.get_optimizer 'SGD')"
@@ -25,8 +30,8 @@ class FusedSGDEMA:
         self.rec = int(lib.u2pl_sgd_tensor_bytes())
         self.chunk = int(lib.u2pl_sgd_chunk_elems())
         assert self.rec == 56
-        self._pin = None
-        self._dev = None
+        self._slots = [dict(pin=None, dev=None, event=None), dict(pin=None, dev=None, event=None)]
+        self._turn = 0
 
     @torch.no_grad()
     def step(self, ema_decay=None):
@@ -41,19 +46,27 @@ class FusedSGDEMA:
             for p in group["params"]:
                 if p.grad is None:
                     continue
-                assert p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous() and p.grad.dtype == torch.float32
+                # The update is element-wise, so any dense layout works as long as parameter, gradient, momentum buffer and
+                # teacher parameter share it (the network's conv weights are channels-last: dense, not "contiguous").
+                assert p.dtype == torch.float32 and _dense(p), "fused SGD needs dense fp32 parameters"
+                g = p.grad
+                if g.dtype != torch.float32 or g.stride() != p.stride():
+                    g = torch.empty_like(p).copy_(g)              # empty_like keeps p's (dense) strides
                 dev = p.device
                 state = self.opt.state[p]
-                first = "momentum_buffer" not in state or state["momentum_buffer"] is None
-                if first:
-                    state["momentum_buffer"] = torch.empty_like(p)
-                m = state["momentum_buffer"]
+                m = state.get("momentum_buffer")
+                first = m is None
+                if first or m.stride() != p.stride():
+                    m = torch.empty_like(p) if first else torch.empty_like(p).copy_(m)
+                    state["momentum_buffer"] = m
                 t = self.pairs.get(id(p)) if (self.pairs is not None and ema_decay is not None) else None
                 if t is not None:
-                    assert t.is_contiguous() and t.dtype == torch.float32 and t.data_ptr() != p.data_ptr()
+                    assert t.dtype == torch.float32 and t.data_ptr() != p.data_ptr()
+                    if t.stride() != p.stride():                  # re-lay the teacher tensor once, in place of the old storage
+                        t.data = torch.empty_like(p).copy_(t.data)
                 n = p.numel()
                 idx = len(recs)
-                recs.append(struct.pack("<QQQQqffii", p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), t.data_ptr() if t is not None else 0,
+                recs.append(struct.pack("<QQQQqffii", p.data_ptr(), g.data_ptr(), m.data_ptr(), t.data_ptr() if t is not None else 0,
                                         n, float(group["lr"]), float(group["weight_decay"]), int(first), 0))
                 chunks.extend((idx, c) for c in range((n + self.chunk - 1) // self.chunk))
         if not recs:
@@ -61,14 +74,26 @@ class FusedSGDEMA:
         table = np.frombuffer(b"".join(recs), dtype=np.uint8)
         ch = np.asarray(chunks, dtype=np.uint32).reshape(-1)
         nbytes = table.size + ch.size * 4
-        if self._pin is None or self._pin.numel() < nbytes:
-            self._pin = torch.empty(nbytes * 2, dtype=torch.uint8)
+        # two pinned staging buffers used alternately: the async H2D copy of step k may still be queued when the host
+        # builds the tables of step k+1 (the host runs ahead of the GPU), so a buffer is rewritten only after ITS copy ran
+        slot = self._slots[self._turn]
+        self._turn ^= 1
+        if slot["pin"] is None or slot["pin"].numel() < nbytes:
+            slot["pin"] = torch.empty(nbytes * 2, dtype=torch.uint8)
             if dev.type == "cuda":                            # (CPU tensors only ever reach here under the tests' emulated ABI)
-                self._pin = self._pin.pin_memory()
-            self._dev = torch.empty(nbytes * 2, dtype=torch.uint8, device=dev)
-        self._pin[:table.size].copy_(torch.from_numpy(table.copy()))
-        self._pin[table.size:nbytes].copy_(torch.from_numpy(ch.view(np.uint8).copy()))
-        self._dev[:nbytes].copy_(self._pin[:nbytes], non_blocking=True)
-        rc = lib.u2pl_sgd_ema_step(_p(self._dev), _p(self._dev[table.size:]), len(chunks), float(momentum),
-                                   float(ema_decay if ema_decay is not None else 0.0), int(ema_decay is not None), _stream())
+                slot["pin"] = slot["pin"].pin_memory()
+            slot["dev"] = torch.empty(nbytes * 2, dtype=torch.uint8, device=dev)
+            slot["event"] = None
+        if slot["event"] is not None:
+            slot["event"].synchronize()
+        pin, dbuf = slot["pin"], slot["dev"]
+        pin[:table.size].copy_(torch.from_numpy(table.copy()))
+        pin[table.size:nbytes].copy_(torch.from_numpy(ch.view(np.uint8).copy()))
+        dbuf[:nbytes].copy_(pin[:nbytes], non_blocking=True)
+        if dev.type == "cuda":
+            slot["event"] = torch.cuda.Event()
+            slot["event"].record()
+        rc = lib.u2pl_sgd_ema_step(_p(dbuf), _p(dbuf[table.size:]), len(chunks), float(momentum),
+                                   float(ema_decay if ema_decay is not None else 0.0),
+                                   float(1 - ema_decay) if ema_decay is not None else 1.0, int(ema_decay is not None), _stream())
         _lib.check(rc, "u2pl_sgd_ema_step")
