@@ -147,3 +147,40 @@ def test_model_bf16_fused_close_to_fp32():
             outbf = mbf(_cl(x))
     for k in ("pred", "rep"):
         assert (outbf[k].float() - out32[k]).norm() <= 0.1 * out32[k].norm(), k
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_conv_bias_in_front_of_batchnorm(k):
+    """decoder.py:60-113 keeps nn.Conv2d's default bias in front of a BatchNorm.  Train mode: the fused path drops the bias
+    pass (the normalised output does not depend on it), corrects the running mean and returns a zero bias gradient;
+    eval mode: the bias is folded into the fused conv epilogue.  Both against the plain modules in fp32."""
+    from u2pl_b200 import fused
+    torch.manual_seed(0)
+    seq = nn.Sequential(nn.Conv2d(64, 128, k, 1, k // 2, bias=True), nn.BatchNorm2d(128), nn.ReLU(inplace=True)).cuda()
+    ref = nn.Sequential(nn.Conv2d(64, 128, k, 1, k // 2, bias=True), nn.BatchNorm2d(128), nn.ReLU(inplace=True)).cuda()
+    with torch.no_grad():
+        seq[0].bias.normal_(0, 2.0)                                 # a bias large enough to matter if mishandled
+    ref.load_state_dict(seq.state_dict())
+    x = torch.randn(4, 64, 33, 37, device="cuda")
+    xb = x.bfloat16().contiguous(memory_format=torch.channels_last)
+    xr = xb.float().requires_grad_(True)
+    xq = xb.clone().requires_grad_(True)
+    seq.train(); ref.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = fused.run_sequential(seq, xq)
+    yr = ref(xr)
+    assert float((y.float() - yr).abs().max()) <= 3e-2 * float(yr.abs().max())
+    g = torch.randn_like(yr)
+    y.backward(g.bfloat16().contiguous(memory_format=torch.channels_last))
+    yr.backward(g)
+    assert float((seq[1].running_mean - ref[1].running_mean).abs().max()) <= 2e-2      # includes momentum * bias
+    assert float((seq[1].running_var - ref[1].running_var).abs().max()) <= 2e-2 * float(ref[1].running_var.abs().max())
+    assert float(seq[0].bias.grad.abs().max()) == 0.0 and float(ref[0].bias.grad.abs().max()) <= 1e-3   # identically / numerically zero
+    assert float((seq[0].weight.grad - ref[0].weight.grad).norm() / ref[0].weight.grad.norm()) <= 3e-2
+    seq.eval(); ref.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ye = fused.run_sequential(seq, xb)
+    with torch.no_grad():
+        ref[1].load_state_dict(seq[1].state_dict())
+        yre = ref(xb.float())
+    assert float((ye.float() - yre).abs().max()) <= 3e-2 * float(yre.abs().max())

@@ -38,6 +38,7 @@ struct SelState {
     float    val[kMaxT];            //                 exact order statistics
     uint32_t band[kMaxT];           //                 candidate band (list / counter index) of every target
     uint32_t bar;                   // fused chain: grid-barrier arrival counter (zeroed with the rest of the state)
+    uint32_t next_block;            // fused chain: dynamic pixel-block scheduler
     unsigned long long stamp[8];    // fused chain: %globaltimer of CTA 0 at the phase boundaries (U2PL_CHAIN_TIMING=1 prints them)
 };
 
@@ -784,7 +785,7 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
 // Three grid barriers replace four launches + three scans.  Soundness argument: see the two-level path (kDelta).
 constexpr int kChainThreads = 768;                        // two CTAs per SM: 1536 threads keep ~40 registers each, like entropy_fast_hist
 constexpr int kChainCtasPerSm = 2;
-constexpr int kChainMaxSlice = 16384;                     // pixels per CTA: 64 KB of keys + 16 KB of class ids
+constexpr int kChainMaxSlice = 24576;                     // pixels per CTA (capacity of the dynamic deal): 48 KB of 16-bit bins
 // Fine histogram: LINEAR in the entropy value, 1024 bins per unit over [0, 4) (an entropy is at most ln C < 4 for
 // C <= 54; the last bin is open-ended).  The error bound kDelta of the fast evaluation is absolute, so is the bin width:
 // a band (bin + 3 kDelta either side) is ~1.6e-3 wide and holds a few thousand of the 4.2 M pixels, where 128 bins per
@@ -866,52 +867,67 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                      uint32_t *__restrict__ hist, SelState *__restrict__ st, uint32_t *__restrict__ lists)
 {
     extern __shared__ uint32_t chain_smem[];
-    uint32_t *s_keys = chain_smem;                         // [slice]
-    uint32_t *s_hist = s_keys + slice;                     // [kFinePad]: fine histogram; later the select histogram
+    // Per pixel the CTA keeps only its 16-bit fine-histogram bin (0xFFFF = ignored).  Full keys and class ids in shared
+    // memory (5 B per pixel, 220 KB per SM) left ~6 KB of L1 and the streaming pass ran at 3.6 TB/s; with 2 B per pixel the
+    // L1 keeps ~100 KB and the pass runs like the stand-alone entropy kernel.  Later phases read ent[] (L2) only for the
+    // ~1 % of pixels whose bin is within one bin of a target / threshold, and re-read the labels once in P4.
+    uint32_t *s_hist = chain_smem;                         // [kFinePad]: fine histogram; later the select histogram
     uint16_t *s_pix = reinterpret_cast<uint16_t *>(s_hist + kFinePad);   // [kCandCap] candidate slice-local index
     uint8_t *s_hit = reinterpret_cast<uint8_t *>(s_pix + kCandCap);      // [kCandCap] candidate band mask (kMaxT <= 8 bands)
-    uint8_t *s_cls = s_hit + kCandCap;                     // [slice] class id of the pixel (255 stands for every ignored one)
+    uint16_t *s_bin = reinterpret_cast<uint16_t *>(s_hit + kCandCap);    // [slice] fine bin of the pixel's FAST entropy
     __shared__ uint32_t warp_tot[32], s_grank[kMaxT], s_tbin[kMaxT], s_tcum[kMaxT], s_band[kMaxT];
-    __shared__ uint32_t s_bcum[kMaxT], s_bcnt[kMaxT], s_blow[kMaxT], s_bbase[kMaxT], s_bpos[kMaxT];
+    __shared__ uint32_t s_bbin[kMaxT], s_bcum[kMaxT], s_bcnt[kMaxT], s_blow[kMaxT], s_bbase[kMaxT], s_bpos[kMaxT];
     __shared__ float s_gamma[kMaxQ], s_lo[kMaxT], s_hi[kMaxT], s_binlo[kMaxT], s_thr[kMaxQ];
-    __shared__ uint32_t s_n, s_cnt, s_sel_prefix, s_sel_rank, s_wide, s_kmin, s_kmax;
+    __shared__ uint32_t s_n, s_cnt, s_sel_prefix, s_sel_rank, s_kmin, s_kmax;
     __shared__ int s_nband;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = 2 * nq;
     const uint32_t G = gridDim.x;
-    // CTA b owns the pixel blocks b, b + G, b + 2G, ... of kChainThreads pixels each (all CTAs sweep the same region of
-    // every class plane at the same time, like a grid-stride kernel: contiguous per-CTA slices made 21 x 296 separate
-    // DRAM streams and cost a third of the bandwidth).  Slice-local index j = k * kChainThreads + tid.
-    const uint32_t nblk = slice / kChainThreads;           // blocks per CTA (slice is a multiple of kChainThreads)
-    const uint32_t cnt = slice;                            // local indices scanned by the later phases; pixels beyond N hold kInvalidKey
-    auto global_of = [&](uint32_t j) { return ((j / kChainThreads) * G + blockIdx.x) * kChainThreads + (j % kChainThreads); };
+    // Pixel blocks of kChainThreads pixels are handed out DYNAMICALLY (atomic counter): all CTAs sweep the same region of
+    // every class plane at the same time, like a grid-stride kernel (contiguous per-CTA slices made 21 x 296 separate DRAM
+    // streams), and an SM that gets less memory bandwidth simply takes fewer blocks (with a static round-robin deal the
+    // slowest CTA finished its 19 blocks 30 us after the fastest).  A CTA keeps at most kMaxBlk blocks (its shared-memory
+    // slice); slice-local index j = k * kChainThreads + tid for the k-th block it took.
+    const uint32_t kMaxBlk = slice / kChainThreads;        // capacity (slice is a multiple of kChainThreads)
+    const uint32_t total_blocks = (N + kChainThreads - 1) / kChainThreads;
+    __shared__ uint32_t s_blk[kChainMaxSlice / kChainThreads + 1];
+    auto global_of = [&](uint32_t j) { return s_blk[j / kChainThreads] * kChainThreads + (j % kChainThreads); };
 
     // ---------------------------------------------------------------- P1
     phase_stamp(st, 0);
     unsigned long long *dbg_t = reinterpret_cast<unsigned long long *>(hist + 5120) + blockIdx.x * 2;   // (U2PL_CHAIN_TIMING) free words of hist2
     if (dbg && tid == 0) { unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); dbg_t[0] = t0; }
     for (int j = tid; j < kFinePad; j += kChainThreads) s_hist[j] = 0;
-    if (tid == 0) s_wide = 0;
     __syncthreads();
-    for (uint32_t k = 0; k < nblk; ++k) {
+    if (tid == 0) s_blk[0] = atomicAdd(&st->next_block, 1u);
+    __syncthreads();
+    uint32_t nblk = 0;
+    for (uint32_t k = 0; k < kMaxBlk; ++k) {
+        const uint32_t blk = s_blk[k];
+        if (blk >= total_blocks) break;
+        nblk = k + 1;
+        if (tid == 0 && k + 1 < kMaxBlk) s_blk[k + 1] = atomicAdd(&st->next_block, 1u);      // next block, one iteration ahead
         const uint32_t j = k * kChainThreads + tid;
-        const uint32_t i = (k * G + blockIdx.x) * kChainThreads + tid;
-        if (i >= N) { s_keys[j] = kInvalidKey; s_cls[j] = 255; continue; }
-        const uint32_t b = i / HW, p = i - b * HW;
-        const float *x = logits + static_cast<size_t>(b) * C * HW + p;
-        float v[C];
+        const uint32_t i = blk * kChainThreads + tid;
+        if (i >= N) {
+            s_bin[j] = 0xFFFFu;
+        } else {
+            const uint32_t b = i / HW, p = i - b * HW;
+            const float *x = logits + static_cast<size_t>(b) * C * HW + p;
+            float v[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
-        const int64_t t = __ldg(target_in + i);
-        const float h = entropy_fast_of<C>(v);
-        ent[i] = h;
-        const bool valid = (t != ignore);
-        const uint32_t key = valid ? float_key(h) : kInvalidKey;
-        s_keys[j] = key;
-        s_cls[j] = valid ? static_cast<uint8_t>(t) : static_cast<uint8_t>(255);
-        if (valid && (t < 0 || t > 254)) s_wide = 1;       // a label that one byte cannot hold: P4 re-reads target_in
-        if (valid && !(dbg & 2)) hist_add(s_hist, fine_bin(h));
+            for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
+            const int64_t t = __ldg(target_in + i);
+            const float h = entropy_fast_of<C>(v);
+            ent[i] = h;
+            const bool valid = (t != ignore);
+            const uint32_t fb = fine_bin(h);
+            s_bin[j] = valid ? static_cast<uint16_t>(fb) : static_cast<uint16_t>(0xFFFFu);
+            if (valid && !(dbg & 2)) hist_add(s_hist, fb);
+        }
+        __syncthreads();                                   // s_blk[k + 1] visible (the barrier stays OUTSIDE the divergent branch)
     }
+    const uint32_t cnt = nblk * kChainThreads;             // local indices scanned by the later phases; pixels beyond N hold kInvalidKey
     __syncthreads();
     for (int j = tid; j < kFineBins; j += kChainThreads)
         if (s_hist[j]) atomicAdd(&hist[j], s_hist[j]);
@@ -974,6 +990,7 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                     s_lo[b] = (bin == 0) ? __uint_as_float(0xff800000u) : fine_lo(bin) - 3.0f * kDelta;
                     s_hi[b] = (bin == kFineBins - 1) ? __uint_as_float(0x7f800000u) : fine_lo(bin + 1) + 3.0f * kDelta;
                     s_bcum[b] = s_tcum[t];                 // valid pixels in lower bins: fast value < s_binlo[b]
+                    s_bbin[b] = bin;
                 }
                 s_band[t] = static_cast<uint32_t>(b);
             }
@@ -997,9 +1014,12 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             __syncthreads();
             const uint32_t te = bounded ? min(cnt, tb + kCandCap) : cnt;
             for (uint32_t j = tb + tid; j < te; j += kChainThreads) {
-                const uint32_t k = s_keys[j];
-                if (k == kInvalidKey) continue;
-                const float h = key_float(k);
+                const uint32_t fb = s_bin[j];
+                if (fb == 0xFFFFu) continue;
+                bool near = false;                         // a band reaches at most into the neighbouring bins (3 kDelta < bin width)
+                for (int u = 0; u < U; ++u) near |= (fb + 1u >= s_bbin[u] && fb <= s_bbin[u] + 1u);
+                if (!near) continue;
+                const float h = __ldcg(ent + global_of(j));
                 uint32_t hit = 0;
                 for (int u = 0; u < U; ++u) hit |= (h >= s_lo[u] && h < s_hi[u]) ? (1u << u) : 0u;
                 if (hit) {
@@ -1013,16 +1033,15 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             for (uint32_t c2 = tid; c2 < nc; c2 += kChainThreads) {       // exact (contract) entropy of the candidates
                 const uint32_t j = s_pix[c2];
                 uint32_t hit = s_hit[c2];
-                const float hfast = key_float(s_keys[j]);
                 const uint32_t i = global_of(j);
+                const float hfast = __ldcg(ent + i);
                 const uint32_t b = i / HW, p = i - b * HW;
                 const float *x = logits + static_cast<size_t>(b) * C * HW + p;
                 float v[C];
 #pragma unroll
                 for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
                 const float e = entropy_of<C>(v);
-                ent[i] = e;
-                s_keys[j] = float_key(e);
+                __stcg(ent + i, e);
                 while (hit) {
                     const int u = __ffs(hit) - 1;
                     hit &= hit - 1;
@@ -1039,7 +1058,7 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             for (uint32_t c2 = tid; c2 < nc; c2 += kChainThreads) {
                 const uint32_t j = s_pix[c2];
                 uint32_t hit = s_hit[c2];
-                const uint32_t ek = s_keys[j];
+                const uint32_t ek = float_key(__ldcg(ent + global_of(j)));    // this thread's own store of the first pass
                 while (hit) {
                     const int u = __ffs(hit) - 1;
                     hit &= hit - 1;
@@ -1141,16 +1160,24 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
     __syncthreads();
     if (target_out != nullptr) {
         const float th = s_thr[part_idx];
-        const bool wide = s_wide != 0;
+        const bool th_nan = !(th == th);                   // violated invariant: no comparison is true, nothing is dropped
+        const uint32_t thb = th_nan ? 0u : fine_bin(th);
         int kept = 0;
         for (uint32_t k = 0; k < nblk; ++k) {
             const uint32_t j = k * kChainThreads + tid;
-            const uint32_t i = (k * G + blockIdx.x) * kChainThreads + tid;
+            const uint32_t i = s_blk[k] * kChainThreads + tid;
             if (i >= N) continue;
-            const uint32_t key = s_keys[j];
-            const bool valid = (key != kInvalidKey);
-            const bool drop = valid && (key_float(key) >= th);
-            const int64_t t = (valid && !drop) ? (wide ? __ldg(target_in + i) : static_cast<int64_t>(s_cls[j])) : ignore;
+            const uint32_t fb = s_bin[j];
+            const bool valid = (fb != 0xFFFFu);
+            // Two or more bins away from the threshold's bin the comparison is decided by the bin alone (stored values differ
+            // from the fast value by <= kDelta, a tenth of a bin); in between the stored value -- exact for every candidate --
+            // is read back.
+            bool drop = false;
+            if (valid && !th_nan) {
+                if (fb > thb + 1u) drop = true;
+                else if (fb + 1u >= thb) drop = (__ldcg(ent + i) >= th);
+            }
+            const int64_t t = (valid && !drop) ? __ldg(target_in + i) : ignore;
             target_out[i] = t;
             if (drop_mask) drop_mask[i] = drop ? 1 : 0;
             kept += (valid && !drop) ? 1 : 0;
@@ -1447,9 +1474,12 @@ static int launch_chain(const float *logits, const int64_t *target_in, uint32_t 
                                                                std::max<long long>(1, (static_cast<long long>(N) + 4095) / 4096)));
     const uint32_t blocks = (N + kChainThreads - 1) / kChainThreads;       // pixel blocks, dealt round-robin to the CTAs
     if (grid > blocks) grid = blocks;
-    uint32_t slice = ((blocks + grid - 1) / grid) * kChainThreads;
+    // capacity of a CTA: its even share + 25 % (dynamic deal), at most kChainMaxSlice
+    uint32_t need = (blocks + grid - 1) / grid;
+    uint32_t slice = std::min<uint32_t>((need + (need + 3) / 4 + 1) * kChainThreads, (kChainMaxSlice / kChainThreads) * kChainThreads);
+    if (static_cast<unsigned long long>(slice / kChainThreads) * grid < blocks) return 0;       // would not cover the tensor
     if (slice > static_cast<uint32_t>(kChainMaxSlice)) return 0;
-    auto smem_for = [](size_t sl) { return sl * 4 + kFinePad * 4 + kCandCap * 3 + sl; };
+    auto smem_for = [](size_t sl) { return kFinePad * 4 + kCandCap * 3 + sl * 2; };
     const size_t smem = smem_for(slice);
     static bool configured = false;
     if (!configured) {

@@ -40,6 +40,11 @@ def _env(name, default):
 #              instead of nine GEMMs over cropped copies of the (large) input: -13 ms per V16 step.
 # "tc_train"   train-mode forward AND data gradient of every eligible stride-1 convolution through conv_tc (statistics in
 #              the epilogue); opt-in: the 1-CTA kernel runs at 0.65 of cuDNN's 2-CTA kernels, the step gets slower.
+# "tc_t2"      train-mode forward WITHOUT autograd (the teacher's second forward, train_semi.py:362-364) of every eligible
+#              stride-1 convolution through the flat tcgen05 kernel with the BatchNorm statistics taken in its epilogue
+#              (no bn_stats pass over the output).
+# "bias_fold"  convolution bias in front of a BatchNorm: folded into the fused epilogue (eval) / dropped from the train-mode
+#              forward with the running mean corrected (`_conv_bias_bn_train`); no separate bias pass either way.
 # "tc_wgrad"   3x3 stride-1 weight gradients of the DilatedConv2d layers via csrc/wgrad_tc.cu (MN-major operands read in
 #              place, 0.74-1.16 PFLOP/s): -4.8 ms of backward per V16 step against the stacked-GEMM form.
 # "tc_chain"   no-grad TRAIN-mode chains (teacher's second forward, train_semi.py:362-364): inner BatchNorm + ReLU applied
@@ -50,6 +55,8 @@ ENABLED = {"bn": True, "wgrad": True,
            "tc_dilated": _env("U2PL_TC_DILATED", "1"),
            "wgrad_stack": _env("U2PL_WGRAD_STACK", "1"),
            "tc_train": _env("U2PL_TC_TRAIN", "0"),
+           "tc_t2": _env("U2PL_TC_T2", "0"),
+           "bias_fold": _env("U2PL_BIAS_FOLD", "1"),
            "tc_wgrad": _env("U2PL_TC_WGRAD", "1"),
            "tc_chain": _env("U2PL_TC_CHAIN", "0"),
            "pool": _env("U2PL_POOL", "1")}
@@ -64,8 +71,8 @@ def _tc_conv_wins(conv, residual):
     bn_apply.  1x1: the epilogue fusion always wins (44 vs 35+30 us at 1024->256; 88 vs 44+150 us at 256->1024 with
     the residual).  3x3: the 1-CTA kernel reaches 1.0-1.2 PF/s against cuDNN's 1.5-1.6 PF/s 2-CTA kernels, so only the
     large dilations (where cuDNN falls back to an sm80 kernel) win."""
-    if ENABLED["tc_conv"] in ("1", True):
-        return True
+    if ENABLED["tc_conv"] in ("1", True, "auto"):   # flat-tile kernel (conv_tc3.cu): at cuDNN's rate on every layer shape, so the
+        return True                                 # fusion of BN (+bias, +residual, +ReLU) always wins; "0" / "1x1" for A/B runs
     if ENABLED["tc_conv"] == "1x1":                            # A/B switch: every 1x1 as well
         return conv.kernel_size == (1, 1) or conv.dilation[0] >= TC_DILATION_MIN
     # measured in the step (gpurun_out/r2b_*): routing every 1x1 of T1 through the 1-CTA kernel made T1 slower (22.1 vs
@@ -221,6 +228,41 @@ class _ConvTCFn(torch.autograd.Function):
         return dx, dw, None, None
 
 
+class _ZeroBiasGrad(torch.autograd.Function):
+    """Identity on y that hands the (unused) bias a zero gradient -- see _conv_bias_bn_train."""
+
+    @staticmethod
+    def forward(ctx, y, bias):
+        ctx.shape, ctx.dev, ctx.dtype = bias.shape, bias.device, bias.dtype
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, torch.zeros(ctx.shape, device=ctx.dev, dtype=ctx.dtype)
+
+
+def _bias_fold_ok(x, conv, bn):
+    return (ENABLED["bias_fold"] and type(conv) is nn.Conv2d and conv.bias is not None and bn.training and _is_cl_bf16(x)
+            and isinstance(bn, (nn.BatchNorm2d, nn.SyncBatchNorm)) and _bn_channels_ok(conv.out_channels, bn))
+
+
+def _conv_bias_bn_train(x, conv, bn, relu, residual):
+    """Train-mode bn(conv(x) + b) without the bias pass (decoder.py:60-113: the heads' 3x3 convolutions and the low-level
+    1x1 projection keep nn.Conv2d's default bias in front of a BatchNorm).  Batch normalisation removes the per-channel
+    mean, so the normalised output does not depend on b, the gradient of b is identically zero (the reference computes
+    rounding noise there; its weight decay still acts, so a zero gradient is returned rather than None), and only the
+    running mean sees b: it is corrected by momentum * b after the statistics kernel updated it from the bias-free sums.
+    Saves one read+write of the 129x129 activation per biased layer and direction (~0.27 ms each at 32 crops)."""
+    w = conv.weight if torch.is_autocast_enabled() else conv.weight.to(x.dtype)      # (autocast casts once per context)
+    y = F.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    if torch.is_grad_enabled() and conv.bias.requires_grad:
+        y = _ZeroBiasGrad.apply(y, conv.bias)
+    out = bn_act(y, bn, relu, residual)
+    with torch.no_grad():
+        bn.running_mean.add_(conv.bias.detach().to(bn.running_mean.dtype), alpha=float(bn.momentum))
+    return out
+
+
 def _tc_geometry_ok(x, conv):
     k, d = conv.kernel_size[0], conv.dilation[0]
     if type(x).__name__ == "_ShapeProxy":             # output of an eligible stride-1 conv: channels-last bf16 by construction
@@ -243,7 +285,7 @@ def _tc_conv_ok(x, conv, bn, residual):
     return (ENABLED["tc_conv"] and not bn.training and not torch.is_grad_enabled() and _is_cl_bf16(x)
             and isinstance(conv, nn.Conv2d) and _tc_conv_wins(conv, residual) and isinstance(bn, (nn.BatchNorm2d, nn.SyncBatchNorm))
             and conv.kernel_size in ((1, 1), (3, 3)) and conv.stride == (1, 1) and conv.dilation == (d, d)
-            and conv.padding == (d * (k // 2), d * (k // 2)) and conv.groups == 1 and conv.bias is None
+            and conv.padding == (d * (k // 2), d * (k // 2)) and conv.groups == 1
             and conv.padding_mode == "zeros" and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0
             and bn.track_running_stats and (residual is None or _is_cl_bf16(residual)))
 
@@ -253,6 +295,13 @@ def conv_bn_act(x, conv, bn, relu=None, residual=None):
     bf16 activations: ONE implicit-GEMM kernel with the folded BatchNorm, the residual and the ReLU in its epilogue;
     otherwise the convolution module followed by `bn_act`."""
     if not _tc_conv_ok(x, conv, bn, residual):
+        if _bias_fold_ok(x, conv, bn):
+            return _conv_bias_bn_train(x, conv, bn, relu, residual)
+        if (ENABLED["tc_t2"] and not torch.is_grad_enabled() and bn.training and isinstance(conv, nn.Conv2d)
+                and _tc_geometry_ok(x, conv) and _bn_channels_ok(conv.out_channels, bn)):
+            from .ops import conv_bf16_nhwc_stats
+            y, sums = conv_bf16_nhwc_stats(x, conv.weight, conv.dilation[0])
+            return bn_act(y, bn, relu, residual, sums=sums)
         if ENABLED["tc_train"] and type(conv) is nn.Conv2d and _tc_geometry_ok(x, conv):   # train mode / autograd on
             if bn.training and _bn_channels_ok(conv.out_channels, bn):
                 y, sums = _ConvTCFn.apply(x, conv.weight.to(torch.bfloat16), conv.dilation[0], True)
@@ -267,6 +316,8 @@ def conv_bn_act(x, conv, bn, relu=None, residual=None):
     shift = torch.empty(C, dtype=torch.float32, device=x.device)
     _lib.check(lib.u2pl_bn_fold(C, _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), float(bn.eps),
                                 _p(scale), _p(shift), _stream()), "u2pl_bn_fold")
+    if conv.bias is not None:                       # bn(conv + b) = conv * scale + (shift + scale * b)
+        shift = torch.addcmul(shift, scale, conv.bias.detach().float())
     return conv_bf16_nhwc(x, conv.weight, conv.dilation[0], scale, shift, residual, relu is not None and relu is not False)
 
 
@@ -363,7 +414,8 @@ def run_sequential(seq, x):
     while i < len(mods):
         m = mods[i]
         if isinstance(m, nn.Conv2d) and i + 1 < len(mods) and isinstance(mods[i + 1], (nn.BatchNorm2d, nn.SyncBatchNorm)) \
-                and (_tc_conv_ok(x, m, mods[i + 1], None)
+                and (_tc_conv_ok(x, m, mods[i + 1], None) or _bias_fold_ok(x, m, mods[i + 1])
+                     or (ENABLED["tc_t2"] and not torch.is_grad_enabled() and mods[i + 1].training and _tc_geometry_ok(x, m))
                      or (ENABLED["tc_train"] and type(m) is nn.Conv2d and _tc_geometry_ok(x, m))):
             nxt = mods[i + 2] if i + 2 < len(mods) else None
             x = conv_bn_act(x, m, mods[i + 1], nxt if isinstance(nxt, nn.ReLU) else None)

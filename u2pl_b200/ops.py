@@ -396,6 +396,25 @@ def conv1x1_bn_relu_eval(x, weight, scale, shift, relu=True):
     return d.view(N, H, W, -1).permute(0, 3, 1, 2)               # channels-last view of [N,Cout,H,W]
 
 
+_W_CACHE = {}          # id(parameter) -> (weakref, version, [Cout,k,k,Cin] bf16 tensor)
+
+
+def kernel_weight(weight):
+    """The [Cout, k, k, Cin] bf16 matrix the convolution kernels read.  For an nn.Parameter the converted copy is cached
+    until the parameter's version counter moves (optimizer / EMA updates bump it; u2pl_b200.optim bumps it explicitly
+    after the fused kernel wrote through raw pointers), so the teacher's two forwards of a step share one conversion."""
+    import weakref
+    if not isinstance(weight, torch.nn.Parameter):
+        return weight.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()     # no copy when already channels-last bf16
+    key = id(weight)
+    hit = _W_CACHE.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2].device == weight.device:
+        return hit[2]
+    wk = weight.detach().to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
+    _W_CACHE[key] = (weakref.ref(weight), weight._version, wk)
+    return wk
+
+
 def conv_bf16_nhwc(x, weight, dilation=1, scale=None, shift=None, residual=None, relu=False):
     """Stride-1 "same" convolution (1x1 or 3x3, padding = dilation * (k // 2)) of a channels-last bf16 activation
     [N,Cin,H,W] as an implicit GEMM on the tensor cores, epilogue act(conv * scale + shift + residual)
@@ -406,7 +425,7 @@ def conv_bf16_nhwc(x, weight, dilation=1, scale=None, shift=None, residual=None,
     Cout, k = weight.shape[0], weight.shape[2]
     assert x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
     assert weight.shape[1] == Cin and weight.shape[3] == k and k in (1, 3)
-    wk = weight.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()           # [Cout,k,k,Cin]; no copy when channels-last
+    wk = kernel_weight(weight)                                                # [Cout,k,k,Cin] bf16; cached per version
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.shape == (N, Cout, H, W) \
             and residual.is_contiguous(memory_format=torch.channels_last)
@@ -426,7 +445,7 @@ def conv_bf16_nhwc_stats(x, weight, dilation=1):
     Cout, k = weight.shape[0], weight.shape[2]
     assert x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
     assert weight.shape[1] == Cin and weight.shape[3] == k and k in (1, 3)
-    wk = weight.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
+    wk = kernel_weight(weight)
     out = torch.empty((N, Cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
     parts = int(lib.u2pl_conv_stat_parts(N, H, W, k))
     part = torch.empty((parts, 2, Cout), dtype=torch.float32, device=x.device)
@@ -466,7 +485,7 @@ def conv_bf16_nhwc_ex(x, weight, dilation=1, in_scale=None, in_shift=None, in_re
     Cout, k = weight.shape[0], weight.shape[2]
     assert x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
     assert weight.shape[1] == Cin and weight.shape[3] == k and k in (1, 3)
-    wk = weight.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
+    wk = kernel_weight(weight)
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.shape == (N, Cout, H, W) \
             and residual.is_contiguous(memory_format=torch.channels_last)

@@ -37,7 +37,7 @@ class FusedSGDEMA:
     def step(self, ema_decay=None):
         """optimizer.step() (+ EMA of the paired teacher parameters with `ema_decay` when given)."""
         lib = _lib.load()
-        recs, chunks = [], []
+        recs, chunks, touched = [], [], []
         momentum = None
         dev = None
         for group in self.opt.param_groups:
@@ -65,6 +65,9 @@ class FusedSGDEMA:
                     if t.stride() != p.stride():                  # re-lay the teacher tensor once, in place of the old storage
                         t.data = torch.empty_like(p).copy_(t.data)
                 n = p.numel()
+                touched.append(p)
+                if t is not None:
+                    touched.append(t)
                 idx = len(recs)
                 recs.append(struct.pack("<QQQQqffii", p.data_ptr(), g.data_ptr(), m.data_ptr(), t.data_ptr() if t is not None else 0,
                                         n, float(group["lr"]), float(group["weight_decay"]), int(first), 0))
@@ -97,3 +100,6 @@ class FusedSGDEMA:
                                    float(ema_decay if ema_decay is not None else 0.0),
                                    float(1 - ema_decay) if ema_decay is not None else 1.0, int(ema_decay is not None), _stream())
         _lib.check(rc, "u2pl_sgd_ema_step")
+        # the kernel wrote through raw pointers: move the version counters so that caches keyed on them (ops.kernel_weight)
+        # and autograd's saved-tensor checks see the update
+        torch.autograd.graph.increment_version(touched)

@@ -111,7 +111,14 @@ class SemiStep:
             ph = self._event()
             teacher.eval()
             with torch.no_grad():
-                pred_t1 = self._net(teacher, image_u)["pred"]
+                dec = getattr(getattr(teacher, "module", teacher), "decoder", None)
+                if dec is not None:
+                    dec.skip_rep = True                                       # only "pred" is read here
+                try:
+                    pred_t1 = self._net(teacher, image_u)["pred"]
+                finally:
+                    if dec is not None:
+                        dec.skip_rep = False
                 if self.fused_up:                                             # bilinear + softmax + max in one kernel
                     logits_u_aug, label_u_aug = ops.up_softmax_max(pred_t1, (h, w))
                 else:

@@ -53,7 +53,9 @@ class dec_deeplabv3_plus(nn.Module):
         low = run_sequential(self.low_conv, stage1)
         fused = torch.cat((low, F.interpolate(deep, size=low.shape[-2:], mode="bilinear", align_corners=True)), dim=1)
         out = {"pred": run_sequential(self.classifier, fused)}
-        if self.rep_head:
+        # `skip_rep` (set by u2pl_b200.step for the teacher's pseudo-label forward, train_semi.py:318-319, which only reads
+        # "pred"): the reference computes the 61 GFLOP/image representation head there and drops the result
+        if self.rep_head and not getattr(self, "skip_rep", False):
             out["rep"] = run_sequential(self.representation, fused)
         return out
 
