@@ -71,7 +71,11 @@ def test_sharded_bank_equals_replicated_bank():
             assert a["loss"] == b["loss"], (a["loss"], b["loss"])                      # same rows, same kernel maths
             assert any(x > 0 for x in a["loss"])
             for ga, gb in zip(a["grad"], b["grad"]):
-                assert (ga is None) == (gb is None) and (ga is None or np.array_equal(ga, gb))
+                # the backward accumulates duplicate anchors (sampling with replacement, loss_helper.py:179-181) with
+                # floating-point atomics: the sum is the same, its rounding order is not reproducible run to run
+                assert (ga is None) == (gb is None)
+                if ga is not None:
+                    assert np.array_equal(ga != 0, gb != 0) and np.allclose(ga, gb, rtol=1e-5, atol=1e-9)
             for ca, cb in zip(a["bank"], b["bank"]):
                 assert np.array_equal(ca, cb)
         for c in range(len(ret[(0, True)]["bank"])):                                   # both ranks see the same bank
