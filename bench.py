@@ -92,10 +92,13 @@ def synth_batch(seed, bl, bu, crop, C):
     return image_l, lab, image_u
 
 
-NETWORK_NOTE = ("channels-last bf16 autocast.  Own kernels (libu2pl_b200.so): BN statistics/apply(+ReLU,+residual)/backward, "
-                "stem max-pool, tcgen05 implicit-GEMM conv for the teacher's eval forward where it beats cuDNN + a BN pass "
-                "(all 1x1, dilation >= 18) and for every dilation >= 18 forward, all losses.  Library (cuDNN/cuBLAS): the "
-                "remaining convolutions, data and weight gradients -- see config.routing")
+NETWORK_NOTE = ("channels-last bf16 autocast.  Own kernels (libu2pl_b200.so): flat-tile tcgen05 implicit-GEMM convolution "
+                "(im2col TMA, BN + bias + residual + ReLU in the epilogue) for every stride-1 convolution of the teacher's "
+                "eval forward (T1: 106 of 113 convolutions, 97 % of its FLOPs) and for the dilation >= 18 forwards of all "
+                "passes; tcgen05 weight gradient (MN-major operands) for the dilated 3x3 layers; BN statistics / apply "
+                "(+ReLU, +residual) / backward; stem max-pool; every loss kernel; SGD + EMA.  Library (cuDNN / cuBLAS): "
+                "train-mode forward of the other convolutions, data gradients, remaining weight gradients -- see "
+                "config.routing (U2PL_TC_TRAIN=1 moves those onto the own kernels too, measured 5 % slower per step)")
 EPOCH, LEN_LOADER = 40, 100                 # V16 mid-training (epoch 40/80): drop_percent 90, alpha_t 10
                                             # (c2 has 200 epochs: epoch 40 -> drop_percent 84, alpha_t 16)
 PEAK = 8.0                                  # scale of the last classifier conv so that random-init teacher
@@ -424,15 +427,16 @@ def our_arm(args):
     traffic = None                                              # dram bytes of the dominant kernel from one `ncu --set full`
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
-            traffic = json.load(fh).get("entropy_fast_hist_kernel_dram_bytes")
+            traffic = json.load(fh).get("entropy_chain_kernel_dram_bytes")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "fused entropy / percentile / partition chain (u2pl_entropy_thresholds_fast: "
-                "entropy_fast_hist, fast_refine, fast_candidate, exact_select; + u2pl_partition_target), 3 percentiles, "
-                "CUDA events on the launching stream inside the timed step",
+    roofline = {"bound": "hbm", "kernel": "entropy_chain_kernel -- ONE cooperative launch for softmax-entropy + three percentile "
+                "thresholds (np.percentile float32 semantics) + reliable/unreliable partition (u2pl_entropy_partition_fused; "
+                "two tiny memsets precede it), CUDA events on the launching stream inside the timed step",
                 "achieved": (alg_bytes / (ep * 1e-6) / 1e9) if ep else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": (alg_bytes / (ep * 1e-6) / 1e9 / peaks["hbm_gbs"]) if ep else None, "traffic": traffic,
-                "traffic_note": "dram read+write of entropy_fast_hist (the dominant kernel of the chain) per launch",
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the same kernel, one launch, ncu --set full "
+                                "(profiles/r02_ncu_summaries.txt); same scope as algorithmic_bytes",
                 "us_per_call": ep, "algorithmic_bytes": alg_bytes, "peak_source": peaks["src"]}
     flop_step = FWD_GFLOP_PER_IMG.get(crop, 651.1) * 1e9 * (bu + 3 * (bl + bu) + (bl + bu))   # T1 + S fwd+bwd(2x) + T2
     tensor = {"bound": "tensor", "scope": "whole step (network = 3 passes)", "achieved": flop_step / (ms_step * 1e-3) / 1e12,
@@ -477,7 +481,7 @@ def our_arm(args):
                        "classifier_peak_scale": PEAK,
                        "bank": "class-sharded, peer-mapped (U2PL_BANK_SHARDED=1)"
                                if world > 1 and os.environ.get("U2PL_BANK_SHARDED", "0") == "1" else "replicated per GPU",
-                       "infonce_depth": int(os.environ.get("U2PL_INFONCE_DEPTH", "1"))},
+                       "infonce_depth": int(os.environ.get("U2PL_INFONCE_DEPTH", "2"))},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": 12 * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "tensor_roofline": tensor,

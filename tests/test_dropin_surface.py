@@ -47,3 +47,12 @@ def test_synthetic_loaders_have_the_driver_shape():
     real = {**cfg, "dataset": {**cfg["dataset"], "synthetic": False, "train": {"data_root": "../../no/such/VOC2012", "crop": {"size": [33, 41]}}}}
     with pytest.raises(NotImplementedError, match="synthetic"):
         get_loader(real)
+
+
+def test_run_semi_runner_check():
+    """The shipped runner for the unchanged reference drivers (python -m u2pl_b200.run_semi) resolves every name the drivers
+    import to the mirror package."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "u2pl_b200.run_semi", "--check"], cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "drop-in surface complete" in out.stdout, out.stderr[-2000:]

@@ -270,3 +270,37 @@ def test_ohem_edge_cases(C, min_kept):
     new_target, _, _ = ops.ohem_select(_dev(x), _dev(target), 0.7, min_kept)
     _, kept = port.ohem_ce(x, target, 0.7, min_kept)
     assert np.array_equal(new_target.cpu().numpy() != 255, kept)
+
+
+def test_v16_index_set_flips_vs_torch_cuda_eager():
+    """north_star: "bit-exact for the integer reliable/unreliable index sets".  Exactness is by construction against the
+    arithmetic contract (oracle); this test QUANTIFIES the distance to the reference's own CUDA arithmetic at BASELINE
+    config-2 size: loss_helper.py:35-43 / train_semi.py:402-418 executed with torch-CUDA ops + np.percentile on the same
+    16 x 21 x 513 x 513 logits, and the number of pixels (of 4 210 704, for each of the three cuts of a step) whose side
+    of the cut differs.  Two libm's agree to ~1e-7, so only pixels inside that band of a threshold can flip."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    B, C, H, W = 16, 21, 513, 513
+    low = torch.randn(B, C, 129, 129, device="cuda", generator=g) * 3
+    low = torch.nn.functional.avg_pool2d(low, 5, 1, 2, count_include_pad=False)
+    x = torch.nn.functional.interpolate(low, (H, W), mode="bilinear", align_corners=True).contiguous()
+    target = x.argmax(1)
+    percents = [90.0, 10.0, 90.0]                                     # drop_percent, alpha_t, 100 - alpha_t at epoch 40/80
+    ent, thresh, _, new_t, n_kept, _ = ops.entropy_partition(x, target, percents, 0)
+    with torch.no_grad():                                             # the reference's arithmetic, on this GPU
+        prob = torch.softmax(x, dim=1)
+        ent_ref = -torch.sum(prob * torch.log(prob + 1e-10), dim=1)
+    e = ent_ref.cpu().numpy().ravel()
+    flips = []
+    for j, q in enumerate(percents):
+        th_ref = np.percentile(e, q)
+        ref_side = ent_ref >= float(th_ref) if j != 1 else ent_ref <= float(th_ref)
+        our_side = ent >= thresh[j] if j != 1 else ent <= thresh[j]
+        flips.append(int((ref_side != our_side).sum().item()))
+        assert abs(float(thresh[j]) - float(th_ref)) <= 2e-6
+    print(f"\n[flip count vs torch-CUDA eager, {B * H * W} pixels] drop-percent cut: {flips[0]}, low-entropy cut: {flips[1]}, "
+          f"high-entropy cut: {flips[2]}; max |entropy - torch| near the cuts <= 2e-6")
+    assert max(flips) <= 64                                           # a handful of tie-band pixels out of 4.2 M
+    ref_target = target.clone()
+    ref_target[ent_ref >= float(np.percentile(e, percents[0]))] = 255
+    assert int((ref_target != new_t).sum().item()) == flips[0]

@@ -577,12 +577,8 @@ infonce_fwd_kernel(InfoNceArgs a)
 // 1 KB row, 51 rows per query).  Arithmetic and its order are unchanged, so results are bit-identical.  Opt-in
 // (U2PL_INFONCE_DEPTH=2|4) until measured.
 template <bool kPeer, int kDepth>
-__global__ void __launch_bounds__(128)
-infonce_fwd_pipelined_kernel(InfoNceArgs a)
+__device__ __forceinline__ void infonce_query_pipelined(const InfoNceArgs &a, const int w, const int lane)
 {
-    const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= a.nact * a.nq) return;
     const int act = w / a.nq;
     const int cls = a.act_class[act];
     // ---- ordinal -> pixel (k-th anchor pixel of class cls in row-major order)
@@ -709,6 +705,16 @@ infonce_fwd_pipelined_kernel(InfoNceArgs a)
     for (int j = 0; j < 8; ++j) gv[j] = coef * ((V[j] * sinv - K0[j]) - proj * av[j]);
     if (c0) *reinterpret_cast<float4 *>(g + d0) = make_float4(gv[0], gv[1], gv[2], gv[3]);
     if (c1) *reinterpret_cast<float4 *>(g + d1) = make_float4(gv[4], gv[5], gv[6], gv[7]);
+}
+
+template <bool kPeer, int kDepth>
+__global__ void __launch_bounds__(128)
+infonce_fwd_pipelined_kernel(InfoNceArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= a.nact * a.nq) return;
+    infonce_query_pipelined<kPeer, kDepth>(a, w, lane);
 }
 
 // sum of per-query losses in a fixed order: loss = scale * sum_q CE_q
@@ -862,7 +868,7 @@ extern "C" int u2pl_bank_append(const float *src_rows, float *bank, int64_t D, c
 
 static int infonce_depth()
 {
-    static const int d = [] { const char *e = getenv("U2PL_INFONCE_DEPTH"); return e ? atoi(e) : 1; }();
+    static const int d = [] { const char *e = getenv("U2PL_INFONCE_DEPTH"); return e ? atoi(e) : 2; }();   // two rows in flight: 75 vs 80 us (config 4)
     return d;
 }
 
@@ -888,6 +894,9 @@ extern "C" int u2pl_infonce_forward(const float *rep, int64_t sn, int64_t sd, in
     a.loss_q = loss_q; a.grad_rows = grad_rows; a.anchor_pix = anchor_pix;
     const int warps = nact * nq;
     const int depth = infonce_depth();
+    // (a persistent grid of fewer warps walking the queries in class order was tried to keep the rows in flight inside the
+    // TLB's reach: 4-12x slower -- each query has ~7 us of dependent look-ups in front of its rows, which only many resident
+    // warps hide; profiles/r02_contra_bench.txt)
     if (depth == 4) infonce_fwd_pipelined_kernel<false, 4><<<(warps + 3) / 4, 128, 0, s>>>(a);
     else if (depth == 2) infonce_fwd_pipelined_kernel<false, 2><<<(warps + 3) / 4, 128, 0, s>>>(a);
     else infonce_fwd_kernel<false><<<(warps + 3) / 4, 128, 0, s>>>(a);

@@ -39,7 +39,9 @@ struct SelState {
     uint32_t band[kMaxT];           //                 candidate band (list / counter index) of every target
     uint32_t bar;                   // fused chain: grid-barrier arrival counter (zeroed with the rest of the state)
     uint32_t next_block;            // fused chain: dynamic pixel-block scheduler
-    unsigned long long stamp[8];    // fused chain: %globaltimer of CTA 0 at the phase boundaries (U2PL_CHAIN_TIMING=1 prints them)
+    uint32_t nkmin[kMaxT];          // fused chain: max over the band's candidates of ~key (zero-initialised minimum)
+    uint32_t kmax[kMaxT];           //              max key
+    unsigned long long stamp[12];    // fused chain: %globaltimer of CTA 0 at the phase boundaries (U2PL_CHAIN_TIMING=1 prints them)
 };
 
 struct Percents { float q[kMaxQ]; int use_rank; uint32_t rank; };   // use_rank: one explicit order statistic instead
@@ -765,24 +767,14 @@ fast_candidate_kernel(const float *__restrict__ logits, const uint32_t *__restri
 
 
 // ====================================================================== the whole chain as ONE cooperative kernel
-// entropy -> percentile thresholds -> reliable/unreliable partition in a single persistent launch (one 1024-thread CTA
-// per SM, cudaLaunchCooperativeKernel so that the software grid barrier below cannot deadlock).  CTA b owns the
-// contiguous pixel slice [b*slice, (b+1)*slice) and keeps, in SHARED MEMORY from the first pass to the last, that slice's
-// order-preserving entropy keys (<= 128 KB) and class ids (1 byte per pixel): the logits are streamed from HBM exactly
-// once, the target is read once, and every later pass reads shared memory instead of re-scanning 16.8 MB of keys and
-// 33.7 MB of labels out of L2 / HBM from separate launches:
-//   P1  fast entropy of the slice (coalesced, C loads in flight per thread) -> ent[], s_keys[], s_cls[] and a FINE
-//       histogram: the top 16 key bits (sign, exponent, 7 mantissa bits = 128 bins per octave) restricted to the range
-//       an entropy can take, [2^-24, 4) -> 3328 bins + two clamp bins, 13 KB.  (A 12-bit histogram needed a second,
-//       10-bit refinement pass over the keys and one more grid barrier to reach the same resolution.)
-//   P2  every CTA (redundantly) selects the bin of each target rank from the merged histogram; a target's candidate band
-//       is its bin widened by 3*kDelta; band test on s_keys; all candidates of the slice are compacted and re-evaluated
-//       AT ONCE under the arithmetic contract (exact value back into ent[] and s_keys[], exact key appended to the band's
-//       global list); pixels surely below a band are only counted
-//   P3  CTA t mod G: exact radix select of target t inside its candidate list
-//   P4  numpy lerp -> thresholds (every CTA, redundantly; CTA 0 publishes) and the partition of the slice from shared
-//       memory: target_out = (entropy >= thresh[part_idx] && valid) ? ignore : class, drop mask, kept count
-// Three grid barriers replace four launches + three scans.  Soundness argument: see the two-level path (kDelta).
+// entropy -> percentile thresholds -> reliable/unreliable partition in a single persistent launch (two 768-thread CTAs per
+// SM, cudaLaunchCooperativeKernel so that the software grid barrier below cannot deadlock).  The logits are streamed from
+// HBM exactly once; per pixel a CTA keeps 16 bits in shared memory (the bin of its fast entropy in a fine histogram), the
+// entropy map itself stays in L2-resident global memory and is touched again only for the ~1 % of pixels near a threshold.
+// Measured history of the design (B200, V16 size, profiles/r02_chain_*): four launches 204 us -> this kernel 120 us; what
+// mattered, in order: linear fine bins (candidates 1e5 -> 5e3), one list reservation per CTA instead of one global atomic
+// per candidate (40 us), 2 B instead of 5 B of shared memory per pixel (L1 kept ~100 KB: streaming pass 111 -> 79 us),
+// bitmap + 16-byte loads in the near scan (21 -> 4.5 us), bulk partition overlapped with the candidate warps.
 constexpr int kChainThreads = 768;                        // two CTAs per SM: 1536 threads keep ~40 registers each, like entropy_fast_hist
 constexpr int kChainCtasPerSm = 2;
 constexpr int kChainMaxSlice = 24576;                     // pixels per CTA (capacity of the dynamic deal): 48 KB of 16-bit bins
@@ -844,19 +836,20 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t cnt, uint32_t *warp
     return base + inc - cnt;
 }
 
-// P1  fast entropy of the slice (coalesced, C loads in flight per thread) -> ent[], s_keys[], s_cls[] and a FINE histogram:
-//     the top 16 key bits (sign, exponent, 7 mantissa bits = 128 bins per octave) restricted to the range an entropy can
-//     take, [2^-24, 4) -> 3328 bins + two clamp bins.
-// P2  every CTA (redundantly) selects the bin of each target rank from the merged histogram -- which also tells how many
-//     valid pixels lie in LOWER bins, so nothing has to be counted per pixel; a target's candidate band is its bin widened
-//     by 3*kDelta; band test on s_keys; the candidates of the slice are compacted and re-evaluated AT ONCE under the
-//     arithmetic contract (exact value back into ent[] and s_keys[]); the CTA reserves its range of each band's global
-//     list with ONE atomic per band (one atomic per candidate serialised ~1e5 same-address atomics in L2: 40 us)
-// P3  CTA t mod G: exact select of target t inside its candidate list -- min/max first, then 11-bit radix digits over the
-//     bits in which the candidates actually differ (they share their leading ~15 bits; a digit they all share would put
-//     every shared-memory atomic on one address)
-// P4  numpy lerp -> thresholds (every CTA, redundantly; CTA 0 publishes) and the partition of the slice from shared
-//     memory: target_out = (entropy >= thresh[part_idx] && valid) ? ignore : class, drop mask, kept count
+// P1  pixel blocks of 768 pixels are dealt dynamically (atomic counter, no block barrier); per pixel: C coalesced loads in
+//     flight, fast entropy (MUFU ex2/lg2) -> ent[], its bin in a LINEAR fine histogram (1024 bins per unit over [0,4))
+//     -> s_bin[] (16 bit) and the CTA's shared-memory histogram, merged into the global one with atomics
+// P2  every CTA (redundantly) scans the merged histogram: the bin of each target rank -- which also tells how many valid
+//     pixels lie in LOWER bins, so nothing is counted per pixel -- and from the partition percentile's bins the range
+//     outside of which a pixel's side of the cut is already certain.  All warps list the pixels whose bin can reach a
+//     candidate band (bin +- 3 kDelta); then warps 0..7 read those entropies back, re-evaluate the candidates AT ONCE under
+//     the arithmetic contract (exact value back into ent[]), reserve the CTA's range of each band's global list with ONE
+//     atomic per band and append the exact keys (+ per-band min / max), while warps 8..23 write target_out / drop_mask
+//     for the 99 % of pixels that are ignored or at least two bins away from the threshold's bins
+// P3  CTA t mod G: exact select of target t inside its candidate list: 11-bit radix digits over the bits in which the
+//     candidates differ (they share their leading ~15 bits; a digit they all share would serialise the shared atomics)
+// P4  numpy lerp -> thresholds (every CTA, redundantly; CTA 0 publishes); the remaining ~1 % of pixels compare their stored
+//     (exact) entropy with the threshold; kept count
 // Three grid barriers replace four launches + three scans.  Soundness argument: see the two-level path (kDelta).
 template <int C>
 __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm)
@@ -876,9 +869,9 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
     uint8_t *s_hit = reinterpret_cast<uint8_t *>(s_pix + kCandCap);      // [kCandCap] candidate band mask (kMaxT <= 8 bands)
     uint16_t *s_bin = reinterpret_cast<uint16_t *>(s_hit + kCandCap);    // [slice] fine bin of the pixel's FAST entropy
     __shared__ uint32_t warp_tot[32], s_grank[kMaxT], s_tbin[kMaxT], s_tcum[kMaxT], s_band[kMaxT];
-    __shared__ uint32_t s_bbin[kMaxT], s_bcum[kMaxT], s_bcnt[kMaxT], s_blow[kMaxT], s_bbase[kMaxT], s_bpos[kMaxT];
+    __shared__ uint32_t s_near[kFineBins / 32], s_bnmin[kMaxT], s_bmax[kMaxT], s_bbin[kMaxT], s_bcum[kMaxT], s_bcnt[kMaxT], s_blow[kMaxT], s_bbase[kMaxT], s_bpos[kMaxT];
     __shared__ float s_gamma[kMaxQ], s_lo[kMaxT], s_hi[kMaxT], s_binlo[kMaxT], s_thr[kMaxQ];
-    __shared__ uint32_t s_n, s_cnt, s_sel_prefix, s_sel_rank, s_kmin, s_kmax;
+    __shared__ uint32_t s_nnear, s_n, s_cnt, s_sel_prefix, s_sel_rank, s_kmin, s_kmax, s_plo, s_phi, s_kept;
     __shared__ int s_nband;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = 2 * nq;
@@ -895,18 +888,34 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
 
     // ---------------------------------------------------------------- P1
     phase_stamp(st, 0);
+    if (blockIdx.x == 0 && tid == 0 && n_kept) *n_kept = 0;     // every CTA adds its count after the third grid barrier
     unsigned long long *dbg_t = reinterpret_cast<unsigned long long *>(hist + 5120) + blockIdx.x * 2;   // (U2PL_CHAIN_TIMING) free words of hist2
     if (dbg && tid == 0) { unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); dbg_t[0] = t0; }
     for (int j = tid; j < kFinePad; j += kChainThreads) s_hist[j] = 0;
     __syncthreads();
-    if (tid == 0) s_blk[0] = atomicAdd(&st->next_block, 1u);
+    // Block ids travel through s_blk[] WITHOUT block barriers: warp 0 claims slot k + 2 when it starts its k-th block and
+    // the other warps spin on a slot only if they run more than two blocks ahead of warp 0 (a barrier per block made all
+    // 24 warps wait for the slowest one 19 times per CTA).  A claim beyond the last block ends the deal: warp 0 marks
+    // every remaining slot.
+    constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+    volatile uint32_t *v_blk = s_blk;
+    for (int k2 = tid; k2 <= static_cast<int>(kMaxBlk); k2 += kChainThreads) s_blk[k2] = kEmpty;
     __syncthreads();
-    uint32_t nblk = 0;
+    auto claim = [&](uint32_t slot) {                      // warp 0, lane 0
+        if (slot >= kMaxBlk) return;
+        const uint32_t got = atomicAdd(&st->next_block, 1u);
+        if (got >= total_blocks) { for (uint32_t z = slot; z < kMaxBlk; ++z) v_blk[z] = total_blocks; }
+        else v_blk[slot] = got;
+    };
+    if (tid == 0) { claim(0); if (v_blk[0] < total_blocks) claim(1); }
     for (uint32_t k = 0; k < kMaxBlk; ++k) {
-        const uint32_t blk = s_blk[k];
+        uint32_t blk = 0;
+        if (lane == 0) {
+            if (wid == 0 && k + 2 < kMaxBlk && v_blk[k + 1] < total_blocks) claim(k + 2);   // (slot k + 1 is warp 0's own, already written)
+            while ((blk = v_blk[k]) == kEmpty) { }
+        }
+        blk = __shfl_sync(0xffffffffu, blk, 0);
         if (blk >= total_blocks) break;
-        nblk = k + 1;
-        if (tid == 0 && k + 1 < kMaxBlk) s_blk[k + 1] = atomicAdd(&st->next_block, 1u);      // next block, one iteration ahead
         const uint32_t j = k * kChainThreads + tid;
         const uint32_t i = blk * kChainThreads + tid;
         if (i >= N) {
@@ -925,8 +934,10 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             s_bin[j] = valid ? static_cast<uint16_t>(fb) : static_cast<uint16_t>(0xFFFFu);
             if (valid && !(dbg & 2)) hist_add(s_hist, fb);
         }
-        __syncthreads();                                   // s_blk[k + 1] visible (the barrier stays OUTSIDE the divergent branch)
     }
+    __syncthreads();
+    uint32_t nblk = 0;
+    while (nblk < kMaxBlk && s_blk[nblk] < total_blocks) ++nblk;
     const uint32_t cnt = nblk * kChainThreads;             // local indices scanned by the later phases; pixels beyond N hold kInvalidKey
     __syncthreads();
     for (int j = tid; j < kFineBins; j += kChainThreads)
@@ -938,9 +949,14 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
 
     // ---------------------------------------------------------------- P2: bins of the target ranks, bands, candidates
     {
+        // The merged histogram is read by all 296 CTAs at the same moment: staged with coalesced 16-byte loads (144 line
+        // requests per CTA; six strided 4-byte loads per thread asked L2 for the same 144 lines 864 times per CTA).
+        for (int k4 = tid; k4 < kFinePad / 4; k4 += kChainThreads)
+            reinterpret_cast<uint4 *>(s_hist)[k4] = __ldcg(reinterpret_cast<const uint4 *>(hist) + k4);
+        __syncthreads();
         uint32_t loc[6], sum = 0;                          // thread t owns bins 6t..6t+5 (the global array is padded to kFinePad)
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { loc[k] = __ldcg(hist + tid * 6 + k); sum += loc[k]; }
+        for (int k = 0; k < 6; ++k) { loc[k] = s_hist[tid * 6 + k]; sum += loc[k]; }
         const uint32_t excl = block_excl_scan(sum, warp_tot);
         if (tid == kChainThreads - 1) s_n = excl + sum;
         __syncthreads();
@@ -977,9 +993,9 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
         __syncthreads();
     }
     const uint32_t n_all = s_n;                            // uniform across the grid (same histogram everywhere)
-    if (n_all != 0) {
-        if (tid == 0) {                                    // merge targets with the same bin into one candidate band
-            int nb = 0;
+    if (tid == 0) {
+        int nb = 0;
+        if (n_all != 0) {                                  // merge targets with the same bin into one candidate band
             for (int t = 0; t < T; ++t) {
                 int b = -1;
                 for (int u = 0; u < t; ++u) if (s_tbin[u] == s_tbin[t]) { b = static_cast<int>(s_band[u]); break; }
@@ -994,31 +1010,64 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                 }
                 s_band[t] = static_cast<uint32_t>(b);
             }
-            s_nband = nb;
             if (blockIdx.x == 0) {
                 st->n = n_all;
                 for (int t = 0; t < T; ++t) { st->grank[t] = s_grank[t]; st->band[t] = s_band[t]; }
                 for (int j = 0; j < nq; ++j) st->gamma[j] = s_gamma[j];
             }
+            // The partition threshold lies between the exact order statistics of targets 2p and 2p+1, each within kDelta of
+            // its bin: every pixel two or more bins outside [plo, phi] is decided now, before the threshold is known.
+            s_plo = min(s_tbin[2 * part_idx], s_tbin[2 * part_idx + 1]);
+            s_phi = max(s_tbin[2 * part_idx], s_tbin[2 * part_idx + 1]);
+        } else {
+            s_plo = 0; s_phi = 0;
         }
-        __syncthreads();
+        s_nband = nb;
+        s_kept = 0;
+        s_nnear = 0;
+        for (int k = 0; k < kFineBins / 32; ++k) s_near[k] = 0;
+        for (int u = 0; u < nb; ++u)
+            for (uint32_t bb = (s_bbin[u] ? s_bbin[u] - 1u : 0u); bb <= min(s_bbin[u] + 1u, static_cast<uint32_t>(kFineBins - 1)); ++bb)
+                s_near[bb >> 5] |= 1u << (bb & 31u);
+    }
+    __syncthreads();
+    if (dbg) phase_stamp(st, 8);
+    // Near scan by ALL warps: eight bins per 16-byte shared-memory load, one bitmap probe each (s_near: the bins a band can
+    // reach -- its own and the two neighbours, 3 kDelta < bin width).  The few hundred slice-local indices it finds go to a
+    // list (the histogram staging area is free again); only those pixels are looked at by the candidate warps below.
+    uint16_t *s_nearlist = reinterpret_cast<uint16_t *>(s_hist);
+    constexpr uint32_t kNearCap = kCandCap;                // so that the candidates of a list round always fit
+    if (s_nband > 0) {
+        for (uint32_t j0 = tid * 8; j0 < cnt; j0 += kChainThreads * 8) {
+            const uint4 pk = *reinterpret_cast<const uint4 *>(s_bin + j0);
+            const uint32_t wv[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t fb = (wv[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+                if (fb >= static_cast<uint32_t>(kFineBins)) continue;                 // ignored pixel
+                if (!((s_near[fb >> 5] >> (fb & 31u)) & 1u)) continue;
+                const uint32_t pos = atomicAdd(&s_nnear, 1u);
+                if (pos < kNearCap) s_nearlist[pos] = static_cast<uint16_t>(j0 + e);
+            }
+        }
+    }
+    __syncthreads();
+    constexpr int kCandThreads = 256;                      // warps 0..7: candidates; warps 8..23: bulk partition
+    if (tid < kCandThreads) {
         const int U = s_nband;
+        const uint32_t nnear = s_nnear;
+        const bool use_list = nnear <= kNearCap;           // else (massive ties): scan the slice in bounded rounds, as below
         // Candidates are compacted (16-bit slice-local index + band mask) and then re-evaluated all at once, one per
         // thread, so the ~3 us latency of an exact evaluation (C strided loads + ~900 dependent issue slots) is paid once.
         // A slice holding more than kCandCap candidates (massive ties) is processed in several rounds of kCandCap keys.
         bool bounded = false;
-        for (uint32_t tb = 0; tb < cnt; ) {
-            __syncthreads();
+        for (uint32_t tb = 0; U > 0 && tb < cnt && !(dbg & 8); ) {       // (dbg & 8: timing experiment without the candidate work -- wrong results)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid == 0) s_cnt = 0;
-            if (tid < kMaxT) { s_bcnt[tid] = 0; s_blow[tid] = 0; s_bpos[tid] = 0; }
-            __syncthreads();
-            const uint32_t te = bounded ? min(cnt, tb + kCandCap) : cnt;
-            for (uint32_t j = tb + tid; j < te; j += kChainThreads) {
-                const uint32_t fb = s_bin[j];
-                if (fb == 0xFFFFu) continue;
-                bool near = false;                         // a band reaches at most into the neighbouring bins (3 kDelta < bin width)
-                for (int u = 0; u < U; ++u) near |= (fb + 1u >= s_bbin[u] && fb <= s_bbin[u] + 1u);
-                if (!near) continue;
+            if (tid < kMaxT) { s_bcnt[tid] = 0; s_blow[tid] = 0; s_bpos[tid] = 0; s_bnmin[tid] = 0; s_bmax[tid] = 0; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const uint32_t te = (bounded && !use_list) ? min(cnt, tb + kCandCap) : cnt;
+            auto test_pixel = [&](uint32_t j) {
                 const float h = __ldcg(ent + global_of(j));
                 uint32_t hit = 0;
                 for (int u = 0; u < U; ++u) hit |= (h >= s_lo[u] && h < s_hi[u]) ? (1u << u) : 0u;
@@ -1026,11 +1075,27 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                     const uint32_t pos = atomicAdd(&s_cnt, 1u);
                     if (pos < kCandCap) { s_pix[pos] = static_cast<uint16_t>(j); s_hit[pos] = static_cast<uint8_t>(hit); }
                 }
+            };
+            if (use_list) {
+                for (uint32_t k2 = tid; k2 < nnear; k2 += kCandThreads) test_pixel(s_nearlist[k2]);
+            } else {
+                for (uint32_t j0 = tb + tid * 8; j0 < te; j0 += kCandThreads * 8) {
+                    const uint4 pk = *reinterpret_cast<const uint4 *>(s_bin + j0);
+                    const uint32_t wv[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const uint32_t fb = (wv[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+                        if (fb >= static_cast<uint32_t>(kFineBins)) continue;
+                        if (!((s_near[fb >> 5] >> (fb & 31u)) & 1u)) continue;
+                        test_pixel(j0 + e);
+                    }
+                }
             }
-            __syncthreads();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (dbg) phase_stamp(st, 6);
             const uint32_t nc = s_cnt;
-            if (nc > kCandCap) { bounded = true; continue; }   // did not fit (only possible for the whole-slice attempt): redo in bounded rounds
-            for (uint32_t c2 = tid; c2 < nc; c2 += kChainThreads) {       // exact (contract) entropy of the candidates
+            if (nc > kCandCap) { bounded = true; continue; }   // did not fit (only possible for a whole-slice scan): redo in bounded rounds
+            for (uint32_t c2 = tid; c2 < nc; c2 += kCandThreads) {        // exact (contract) entropy of the candidates
                 const uint32_t j = s_pix[c2];
                 uint32_t hit = s_hit[c2];
                 const uint32_t i = global_of(j);
@@ -1042,20 +1107,25 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
                 for (int c = 0; c < C; ++c) v[c] = __ldg(x + static_cast<size_t>(c) * HW);
                 const float e = entropy_of<C>(v);
                 __stcg(ent + i, e);
+                const uint32_t ek0 = float_key(e);
                 while (hit) {
                     const int u = __ffs(hit) - 1;
                     hit &= hit - 1;
                     atomicAdd(&s_bcnt[u], 1u);
+                    atomicMax(&s_bnmin[u], ~ek0);
+                    atomicMax(&s_bmax[u], ek0);
                     if (hfast < s_binlo[u]) atomicAdd(&s_blow[u], 1u);     // counted in s_bcum although it is a candidate
                 }
             }
-            __syncthreads();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid < U && s_bcnt[tid]) {                  // ONE global atomic per band per CTA reserves the list range
                 s_bbase[tid] = atomicAdd(&st->cnt[tid], s_bcnt[tid]);
                 if (s_blow[tid]) atomicAdd(&st->below[tid], s_blow[tid]);
+                atomicMax(&st->nkmin[tid], s_bnmin[tid]);
+                atomicMax(&st->kmax[tid], s_bmax[tid]);
             }
-            __syncthreads();
-            for (uint32_t c2 = tid; c2 < nc; c2 += kChainThreads) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (uint32_t c2 = tid; c2 < nc; c2 += kCandThreads) {
                 const uint32_t j = s_pix[c2];
                 uint32_t hit = s_hit[c2];
                 const uint32_t ek = float_key(__ldcg(ent + global_of(j)));    // this thread's own store of the first pass
@@ -1067,6 +1137,41 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             }
             tb = te;
         }
+        if (dbg) phase_stamp(st, 7);
+    } else if (target_out != nullptr && !(dbg & 4)) {      // (dbg & 4: timing experiment without the bulk partition -- wrong results)
+        // Bulk partition, overlapped with the latency-bound candidate work of warps 0..7: every pixel that is ignored or
+        // lies two or more bins away from the threshold's bins (99 % of them) gets its output now.
+        const uint32_t plo = s_plo, phi = s_phi;
+        const int bt = tid - kCandThreads, nbt = kChainThreads - kCandThreads;
+        int kept = 0;
+        for (uint32_t j0 = bt; j0 < cnt; j0 += 4 * nbt) {  // four independent label loads in flight per thread
+            uint32_t ii[4];
+            int dec[4];                                    // 0 = ignored / dropped, 1 = kept, 2 = not decided here
+            int64_t lab[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t j = j0 + e * nbt;
+                dec[e] = 2; ii[e] = 0; lab[e] = ignore;
+                if (j < cnt) {
+                    ii[e] = global_of(j);
+                    const uint32_t fb = s_bin[j];
+                    if (ii[e] >= N) dec[e] = 2;
+                    else if (fb == 0xFFFFu) dec[e] = 3;    // ignored pixel: output `ignore`, not counted as dropped
+                    else if (fb > phi + 1u) dec[e] = 0;
+                    else if (fb + 1u < plo) dec[e] = 1;
+                }
+                if (dec[e] == 1) lab[e] = __ldg(target_in + ii[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (dec[e] == 2) continue;
+                target_out[ii[e]] = lab[e];
+                if (drop_mask) drop_mask[ii[e]] = dec[e] == 0 ? 1 : 0;
+                kept += dec[e] == 1 ? 1 : 0;
+            }
+        }
+        kept = warp_sum_i(kept);
+        if (lane == 0 && kept) atomicAdd(&s_kept, static_cast<uint32_t>(kept));
     }
     grid_barrier(&st->bar, 2 * G);
     phase_stamp(st, 3);
@@ -1084,22 +1189,7 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
             if (tid == 0) st->val[t] = __uint_as_float(0x7fc00000u);
             continue;
         }
-        uint32_t kmin = 0xffffffffu, kmax = 0u;
-        for (uint32_t j0 = tid; j0 < n; j0 += 4 * kChainThreads) {       // four independent L2 loads in flight per thread
-            uint32_t kk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) kk[e] = (j0 + e * kChainThreads < n) ? __ldcg(list + j0 + e * kChainThreads) : __ldcg(list + tid % n);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { kmin = min(kmin, kk[e]); kmax = max(kmax, kk[e]); }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-        }
-        if (tid == 0) { s_kmin = 0xffffffffu; s_kmax = 0u; s_sel_prefix = 0; s_sel_rank = r0; }
-        __syncthreads();
-        if (lane == 0) { atomicMin(&s_kmin, kmin); atomicMax(&s_kmax, kmax); }
+        if (tid == 0) { s_kmin = ~__ldcg(&st->nkmin[u]); s_kmax = __ldcg(&st->kmax[u]); s_sel_prefix = 0; s_sel_rank = r0; }   // (min / max gathered in P2)
         __syncthreads();
         const uint32_t diff = s_kmin ^ s_kmax;
         const int nb = diff ? 32 - __clz(diff) : 0;        // the candidates agree on their leading 32 - nb bits
@@ -1160,37 +1250,23 @@ entropy_chain_kernel(const float *__restrict__ logits, const int64_t *__restrict
     __syncthreads();
     if (target_out != nullptr) {
         const float th = s_thr[part_idx];
-        const bool th_nan = !(th == th);                   // violated invariant: no comparison is true, nothing is dropped
-        const uint32_t thb = th_nan ? 0u : fine_bin(th);
+        const bool th_nan = !(th == th);                   // violated invariant (thresholds are NaN): nothing more is dropped
+        const uint32_t plo = s_plo, phi = s_phi;
         int kept = 0;
-        for (uint32_t k = 0; k < nblk; ++k) {
-            const uint32_t j = k * kChainThreads + tid;
-            const uint32_t i = s_blk[k] * kChainThreads + tid;
-            if (i >= N) continue;
+        for (uint32_t j = tid; n_all != 0 && j < cnt; j += kChainThreads) {
             const uint32_t fb = s_bin[j];
-            const bool valid = (fb != 0xFFFFu);
-            // Two or more bins away from the threshold's bin the comparison is decided by the bin alone (stored values differ
-            // from the fast value by <= kDelta, a tenth of a bin); in between the stored value -- exact for every candidate --
-            // is read back.
-            bool drop = false;
-            if (valid && !th_nan) {
-                if (fb > thb + 1u) drop = true;
-                else if (fb + 1u >= thb) drop = (__ldcg(ent + i) >= th);
-            }
-            const int64_t t = (valid && !drop) ? __ldg(target_in + i) : ignore;
-            target_out[i] = t;
+            if (fb == 0xFFFFu || fb > phi + 1u || fb + 1u < plo) continue;       // decided in P2
+            const uint32_t i = global_of(j);
+            if (i >= N) continue;
+            const bool drop = !th_nan && (__ldcg(ent + i) >= th);                // the stored value is exact for every candidate
+            target_out[i] = drop ? ignore : __ldg(target_in + i);
             if (drop_mask) drop_mask[i] = drop ? 1 : 0;
-            kept += (valid && !drop) ? 1 : 0;
+            kept += drop ? 0 : 1;
         }
         kept = warp_sum_i(kept);
+        if (lane == 0 && kept) atomicAdd(&s_kept, static_cast<uint32_t>(kept));
         __syncthreads();
-        if (lane == 0) warp_tot[wid] = static_cast<uint32_t>(kept);
-        __syncthreads();
-        if (tid == 0) {
-            unsigned long long s2 = 0;
-            for (int w = 0; w < kChainThreads / 32; ++w) s2 += warp_tot[w];
-            if (s2) atomicAdd(n_kept, s2);
-        }
+        if (tid == 0 && s_kept) atomicAdd(n_kept, static_cast<unsigned long long>(s_kept));
     }
     phase_stamp(st, 5);
 }
@@ -1508,6 +1584,8 @@ static int launch_chain(const float *logits, const int64_t *target_in, uint32_t 
         SelState h;
         cudaStreamSynchronize(s);
         cudaMemcpy(&h, w.st, sizeof(SelState), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[entropy_chain] P2 of CTA 0: histogram scan %.1f us | band test %.1f us | exact evaluation + list append %.1f us | wait at barrier 2 %.1f us\n",
+                (h.stamp[8] - h.stamp[2]) * 1e-3, (h.stamp[6] - h.stamp[8]) * 1e-3, (h.stamp[7] - h.stamp[6]) * 1e-3, (h.stamp[3] - h.stamp[7]) * 1e-3);
         fprintf(stderr, "[entropy_chain] grid %u slice %u | P1 %.1f us | bar1 %.1f | P2+bar2 %.1f | P3+bar3 %.1f | P4 %.1f | total %.1f us (CTA 0)\n",
                 grid, slice, (h.stamp[1] - h.stamp[0]) * 1e-3, (h.stamp[2] - h.stamp[1]) * 1e-3, (h.stamp[3] - h.stamp[2]) * 1e-3,
                 (h.stamp[4] - h.stamp[3]) * 1e-3, (h.stamp[5] - h.stamp[4]) * 1e-3, (h.stamp[5] - h.stamp[0]) * 1e-3);
@@ -1545,8 +1623,7 @@ extern "C" int u2pl_entropy_partition_fused(const float *logits, const int64_t *
         EntropyWs w;
         uint32_t *lists = nullptr;
         fast_ws_layout(B * HW, ws, &w, &lists);
-        cudaError_t e = cudaMemsetAsync(w.hist1, 0, w.zero_bytes, s);
-        if (e == cudaSuccess) e = cudaMemsetAsync(n_kept, 0, sizeof(int64_t), s);
+        cudaError_t e = cudaMemsetAsync(w.hist1, 0, w.zero_bytes, s);      // (n_kept is zeroed by the kernel itself / the fallback path)
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return static_cast<int>(e); }
         Percents pc;
         pc.use_rank = 0; pc.rank = 0;
