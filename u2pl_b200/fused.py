@@ -175,7 +175,11 @@ class _BNAct(torch.autograd.Function):
 def bn_act(x, bn, relu=None, residual=None, sums=None):
     """relu: an nn.ReLU module (or True) to fuse, or None.  residual: tensor added before the ReLU.
     sums: optional [2,C] batch sums of x from the producing convolution's epilogue (train mode)."""
-    if _bn_ok(x, bn) and (residual is None or _is_cl_bf16(residual)):
+    # (eval mode with autograd on -- frozen-BN fine-tuning, input gradients -- goes through the module: the fused eval
+    # path keeps nothing for a backward pass)
+    needs_eval_grad = (not bn.training) and torch.is_grad_enabled() and (x.requires_grad or bn.weight.requires_grad
+                                                                         or (residual is not None and residual.requires_grad))
+    if _bn_ok(x, bn) and (residual is None or _is_cl_bf16(residual)) and not needs_eval_grad:
         sync = isinstance(bn, nn.SyncBatchNorm) and bn.training and _world() > 1
         return _BNAct.apply(x, bn.weight, bn.bias, residual, bn, relu is not None and relu is not False, sync,
                             sums if bn.training else None)
