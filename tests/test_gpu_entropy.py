@@ -304,3 +304,46 @@ def test_v16_index_set_flips_vs_torch_cuda_eager():
     ref_target = target.clone()
     ref_target[ent_ref >= float(np.percentile(e, percents[0]))] = 255
     assert int((ref_target != new_t).sum().item()) == flips[0]
+
+
+def test_full_size_c2_properties():
+    """BASELINE config 3 per-GPU size (2 x 19 x 769 x 769, OHEM thresh 0.7 / min_kept 100000, contrastive prep to 193 x 193):
+    size-independent checks at full size.  (1) one-launch chain == multi-launch path (thresholds bitwise, target / mask /
+    counts equal, every threshold comparison equal) and np.percentile of the entropies == the on-device thresholds;
+    (2) OHEM: the kept set is {valid, prob_of_target <= max(thresh, k-th smallest)} and holds >= min_kept pixels;
+    (3) low-resolution masks == nearest-neighbour sampling of the full-resolution comparisons (train_semi.py:417-437)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(769)
+    B, C, H, W, h, w = 2, 19, 769, 769, 193, 193
+    low = torch.randn(B, C, h, w, device="cuda", generator=g) * 3
+    low = torch.nn.functional.avg_pool2d(low, 5, 1, 2, count_include_pad=False)
+    x = torch.nn.functional.interpolate(low, (H, W), mode="bilinear", align_corners=True).contiguous()
+    target = x.argmax(1)
+    target[:, :10] = 255                                               # a border of ignored pixels, as in the synthetic labels
+    percents = [84.0, 16.0, 84.0]                                      # drop_percent / alpha_t / 100 - alpha_t at epoch 40 of 200
+    ent, thresh, t_f, n_kept = _fused_vs_two_step(ops, x, target, percents, 0)
+    e = ent.cpu().numpy().ravel()
+    valid = (target != 255).cpu().numpy().ravel()
+    th = thresh.cpu().numpy()
+    for j, q in enumerate(percents):
+        assert th[j] == np.percentile(e[valid], q), q
+    assert n_kept.item() == int(((e < th[0]) & valid).sum()) == int((t_f != 255).sum().item())
+    # (2) OHEM at this size
+    pred = torch.randn(B, C, H, W, device="cuda", generator=g)
+    new_target, kth, n_valid = ops.ohem_select(pred, target, 0.7, 100000)
+    prob = torch.softmax(pred, 1).gather(1, target.clamp(max=C - 1).unsqueeze(1)).squeeze(1)
+    kept = new_target != 255
+    cut = max(0.7, float(kth))
+    band = (prob - cut).abs() <= 2e-6                                  # torch's softmax vs the contract arithmetic near the cut
+    assert int(kept.sum()) >= min(100000, int(n_valid))
+    assert bool(((kept == ((prob <= cut) & (target != 255))) | band).all())
+    # (3) contrastive prep against nearest sampling of the full-resolution comparisons
+    label_l = target.clone()
+    bits, low_m, high_m = ops.contra_prep_lowres(label_l, target, ent, thresh, 1, 2, (h, w), C, True)
+    iy = torch.clamp((torch.arange(h, device="cuda").float() * np.float32(H / h)).floor().long(), max=H - 1)
+    ix = torch.clamp((torch.arange(w, device="cuda").float() * np.float32(W / w)).floor().long(), max=W - 1)
+    samp = lambda t: t[:, iy][:, :, ix]                                # noqa: E731  F.interpolate(mode="nearest") source indices
+    want_low = ((ent <= thresh[1]) & (target != 255)).float()
+    want_high = ((ent >= thresh[2]) & (target != 255)).float()
+    assert torch.equal(low_m[B:, 0], samp(want_low)) and torch.equal(high_m[B:, 0], samp(want_high))
+    assert torch.equal(low_m[:B, 0], samp((label_l != 255).float()))
