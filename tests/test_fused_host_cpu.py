@@ -63,3 +63,51 @@ def test_dgrad_weight_identity(k, d):
     y.backward(g)
     dx = F.conv2d(g, fused.dgrad_weight(w), None, 1, pad, d)
     assert torch.allclose(dx, x.grad, atol=1e-4)
+
+
+def test_bias_free_train_conv_in_front_of_batchnorm_equals_modules():
+    """fused._conv_bias_bn_train (decoder.py:60-113: nn.Conv2d's default bias in front of a BatchNorm): same normalised
+    output, running statistics and weight gradient as the plain modules, a ZERO bias gradient (the reference's is rounding
+    noise around zero), on the CPU in fp32 where bn_act runs the module itself."""
+    import torch.nn as nn
+    from u2pl_b200 import fused
+    torch.manual_seed(3)
+    conv, bn, relu = nn.Conv2d(8, 16, 3, 1, 1, bias=True), nn.BatchNorm2d(16), nn.ReLU()
+    conv_r, bn_r = nn.Conv2d(8, 16, 3, 1, 1, bias=True), nn.BatchNorm2d(16)
+    with torch.no_grad():
+        conv.bias.normal_(0, 2.0)
+    conv_r.load_state_dict(conv.state_dict())
+    bn_r.load_state_dict(bn.state_dict())
+    x = torch.randn(3, 8, 9, 11)
+    y = fused._conv_bias_bn_train(x, conv, bn, relu, None)
+    yr = torch.relu(bn_r(conv_r(x)))
+    assert torch.allclose(y, yr, atol=1e-5)
+    assert torch.allclose(bn.running_mean, bn_r.running_mean, atol=1e-6) and torch.allclose(bn.running_var, bn_r.running_var, atol=1e-6)
+    g = torch.randn_like(yr)
+    y.backward(g)
+    yr.backward(g)
+    assert torch.allclose(conv.weight.grad, conv_r.weight.grad, atol=1e-4)
+    assert float(conv.bias.grad.abs().max()) == 0.0 and float(conv_r.bias.grad.abs().max()) <= 1e-4
+    assert torch.allclose(bn.weight.grad, bn_r.weight.grad, atol=1e-4) and torch.allclose(bn.bias.grad, bn_r.bias.grad, atol=1e-4)
+
+
+def test_kernel_weight_cache_follows_the_version_counter():
+    """ops.kernel_weight caches the [Cout,k,k,Cin] bf16 copy of a Parameter until its version counter moves: in-place
+    updates (optimizer / EMA) and the explicit bump u2pl_b200.optim applies after the fused kernel wrote through raw
+    pointers both invalidate it; plain tensors are never cached."""
+    from u2pl_b200 import ops
+    w = torch.nn.Parameter(torch.randn(4, 8, 3, 3))
+    a = ops.kernel_weight(w)
+    assert a.shape == (4, 3, 3, 8) and a.dtype == torch.bfloat16 and ops.kernel_weight(w) is a
+    with torch.no_grad():
+        w.mul_(2.0)
+    b = ops.kernel_weight(w)
+    assert b is not a and torch.equal(b, (w.detach().to(torch.bfloat16)).permute(0, 2, 3, 1).contiguous())
+    with torch.no_grad():
+        w.data.view(-1)[0] = 7.0                                  # a write the counter does not see (what a raw-pointer kernel does)
+    assert ops.kernel_weight(w) is b
+    torch.autograd.graph.increment_version(w)
+    c = ops.kernel_weight(w)
+    assert c is not b and float(c.reshape(-1)[0]) == 7.0
+    t = torch.randn(4, 8, 1, 1)
+    assert ops.kernel_weight(t) is not ops.kernel_weight(t)

@@ -262,8 +262,9 @@ def _conv_bias_bn_train(x, conv, bn, relu, residual):
     if torch.is_grad_enabled() and conv.bias.requires_grad:
         y = _ZeroBiasGrad.apply(y, conv.bias)
     out = bn_act(y, bn, relu, residual)
-    with torch.no_grad():
-        bn.running_mean.add_(conv.bias.detach().to(bn.running_mean.dtype), alpha=float(bn.momentum))
+    # (through .data: the module path of bn_act -- CPU / fp32 -- hands running_mean to native_batch_norm, whose train-mode
+    # backward never reads it but whose saved-tensor version check would trip over a tracked in-place update)
+    bn.running_mean.data.add_(conv.bias.detach().to(bn.running_mean.dtype), alpha=float(bn.momentum))
     return out
 
 
