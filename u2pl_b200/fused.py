@@ -80,15 +80,15 @@ def _tc_conv_wins(conv, residual):
     return conv.kernel_size == (3, 3) and conv.dilation[0] >= TC_DILATION_MIN
 
 
-def _world():
-    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+def _world(group=None):
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
 
-def _sync_sum_(sums):
+def _sync_sum_(sums, group=None):
     """Cross-rank sum of a [2,C] statistics tensor: one single-CTA kernel over peer-mapped memory on an NVSwitch box
     (csrc/peer_reduce.cu), torch.distributed otherwise."""
     from .peer import allreduce_small_
-    return allreduce_small_(sums)
+    return allreduce_small_(sums, group)                 # (a SyncBatchNorm built on a sub-group exchanges inside it, over NCCL)
 
 
 def _is_cl_bf16(x):
@@ -130,8 +130,9 @@ class _BNAct(torch.autograd.Function):
             else:                                      # statistics already accumulated by the producing conv's epilogue
                 sums = sums_in
             if sync:                                   # SyncBN: global sums; every rank holds the same number of
-                _sync_sum_(sums)                       # pixels (same per-GPU batch and crop, as in the reference configs)
-                count = float(M) * _world()
+                group = getattr(bn, "process_group", None)
+                _sync_sum_(sums, group)                # pixels (same per-GPU batch and crop, as in the reference configs)
+                count = float(M) * _world(group)
             mean = torch.empty(C, dtype=torch.float32, device=dev)
             invstd = torch.empty(C, dtype=torch.float32, device=dev)
             _lib.check(lib.u2pl_bn_finalize(_p(sums), C, ctypes.c_double(count), _p(weight), _p(bias),
@@ -148,6 +149,7 @@ class _BNAct(torch.autograd.Function):
         if training and any(ctx.needs_input_grad):
             ctx.save_for_backward(x, y if relu else None, weight, mean, invstd)
             ctx.meta = (M, C, count, sync, residual is not None, relu)
+            ctx.group = getattr(bn, "process_group", None) if sync else None
         return y
 
     @staticmethod
@@ -162,7 +164,7 @@ class _BNAct(torch.autograd.Function):
                                                _stream()), "u2pl_bn_backward_reduce")
         dweight, dbias = sums[1].clone(), sums[0].clone()            # local sums = this rank's parameter gradients
         if sync:
-            _sync_sum_(sums)
+            _sync_sum_(sums, ctx.group)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
         coef = torch.empty((3, C), dtype=torch.float32, device=dev)
@@ -180,7 +182,7 @@ def bn_act(x, bn, relu=None, residual=None, sums=None):
     needs_eval_grad = (not bn.training) and torch.is_grad_enabled() and (x.requires_grad or bn.weight.requires_grad
                                                                          or (residual is not None and residual.requires_grad))
     if _bn_ok(x, bn) and (residual is None or _is_cl_bf16(residual)) and not needs_eval_grad:
-        sync = isinstance(bn, nn.SyncBatchNorm) and bn.training and _world() > 1
+        sync = isinstance(bn, nn.SyncBatchNorm) and bn.training and _world(getattr(bn, "process_group", None)) > 1
         return _BNAct.apply(x, bn.weight, bn.bias, residual, bn, relu is not None and relu is not False, sync,
                             sums if bn.training else None)
     if x.is_cuda:
@@ -366,9 +368,10 @@ def _finalize_train_bn(bn, sums, count):
     lib = _lib.load()
     C = bn.num_features
     dev = sums.device
-    if isinstance(bn, nn.SyncBatchNorm) and _world() > 1:
-        _sync_sum_(sums)
-        count = count * _world()
+    group = getattr(bn, "process_group", None)
+    if isinstance(bn, nn.SyncBatchNorm) and _world(group) > 1:
+        _sync_sum_(sums, group)
+        count = count * _world(group)
     mean, invstd = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
     scale, shift = torch.empty(C, dtype=torch.float32, device=dev), torch.empty(C, dtype=torch.float32, device=dev)
     _lib.check(lib.u2pl_bn_finalize(_p(sums), C, ctypes.c_double(float(count)), _p(bn.weight), _p(bn.bias), _p(bn.running_mean),
