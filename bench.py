@@ -94,7 +94,7 @@ def synth_batch(seed, bl, bu, crop, C):
 
 NETWORK_NOTE = ("channels-last bf16 autocast.  Own kernels (libu2pl_b200.so): flat-tile tcgen05 implicit-GEMM convolution "
                 "(im2col TMA, BN + bias + residual + ReLU in the epilogue) for every stride-1 convolution of the teacher's "
-                "eval forward (T1: 106 of 113 convolutions, 97 % of its FLOPs) and for the dilation >= 18 forwards of all "
+                "eval forward (T1: 106 of 116 convolutions, 97 % of its FLOPs) and for the dilation >= 18 forwards of all "
                 "passes; tcgen05 weight gradient (MN-major operands) for the dilated 3x3 layers; BN statistics / apply "
                 "(+ReLU, +residual) / backward; stem max-pool; every loss kernel; SGD + EMA.  Library (cuDNN / cuBLAS): "
                 "train-mode forward of the other convolutions, data gradients, remaining weight gradients -- see "
