@@ -185,3 +185,59 @@ def test_maxpool_tap_rule_matches_aten():
                             if tap is None or v > best:
                                 best, tap = v, (h, w)
                     assert best == float(out[n, c, ho, wo]) and tap[0] * W + tap[1] == int(idx[n, c, ho, wo])
+
+
+def _im2col_tile(x_nhwc, m0, tap_r, tap_s, dil, pad, kb, rows=128, kch=64):
+    """What ONE im2col-mode TMA load of conv_tc3.cu delivers (validated against the hardware by the GPU self-test): `rows`
+    consecutive anchors of the bounding box (the image shifted by -pad), walked W first, then H, then N, starting at the
+    tile's first pixel; every anchor reads pixel (anchor + tap offset) with offset {s*dil, r*dil}; channels [64 kb, 64 kb + 64);
+    anything outside the tensor (padding, channel tail, anchors beyond the last image) is zero."""
+    import numpy as np
+    N, H, W, C = x_nhwc.shape
+    out = np.zeros((rows, kch), np.float32)
+    for i in range(rows):
+        m = m0 + i
+        n, rem = divmod(m, H * W)
+        h, w = divmod(rem, W)
+        if n >= N:
+            continue                                                   # M tail: anchors past the last image
+        hh, ww = (h - pad) + tap_r * dil, (w - pad) + tap_s * dil      # start coordinate {w0 - pad, h0 - pad} + instruction offsets
+        if 0 <= hh < H and 0 <= ww < W:
+            c0 = kb * kch
+            c1 = min(C, c0 + kch)
+            out[i, :c1 - c0] = x_nhwc[n, hh, ww, c0:c1]
+    return out
+
+
+@pytest.mark.parametrize("N,C,H,W,Co,k,d", [(2, 72, 9, 11, 40, 3, 2), (3, 64, 7, 5, 24, 3, 1), (1, 136, 13, 6, 8, 1, 1), (2, 64, 5, 5, 16, 3, 4)])
+def test_flat_tile_im2col_addressing_model(N, C, H, W, Co, k, d):
+    """conv_tc3.cu's producer loop as numpy: flat 128-pixel tiles (straddling rows and images), tap-outer / channel-block-inner
+    K order with weight columns tap*Cin + 64 kb (a last block of a tap that runs into the next tap's columns meets zero-filled
+    A channels), dilation, padding = dilation * (k // 2) -- summed over all K steps it must equal F.conv2d."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(N * 100 + C)
+    x = rng.standard_normal((N, H, W, C)).astype(np.float32)
+    wgt = rng.standard_normal((Co, k, k, C)).astype(np.float32)                        # [Cout, r, s, Cin] = the kernel's weight matrix rows
+    wmat = wgt.reshape(Co, k * k * C)
+    pad = d * (k // 2)
+    M = N * H * W
+    kb_per_tap = (C + 63) // 64
+    got = np.zeros((M, Co), np.float32)
+    for m0 in range(0, M, 128):
+        acc = np.zeros((128, Co), np.float32)
+        for tap in range(k * k):
+            r, s = divmod(tap, k)
+            for kb in range(kb_per_tap):
+                a = _im2col_tile(x, m0, r, s, d, pad, kb) if k == 3 else _im2col_tile(x, m0, 0, 0, 1, 0, kb)
+                col0 = tap * C + kb * 64
+                b = np.zeros((Co, 64), np.float32)
+                c1 = min(k * k * C, col0 + 64)
+                b[:, :c1 - col0] = wmat[:, col0:c1]                                    # TMA zero-fills columns beyond K
+                acc += a @ b.T
+        rows = min(128, M - m0)
+        got[m0:m0 + rows] = acc[:rows]
+    ref = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(wgt).permute(0, 3, 1, 2), None, 1, pad, d)
+    ref = ref.permute(0, 2, 3, 1).reshape(M, Co).numpy()
+    assert np.abs(got - ref).max() <= 1e-3 * max(1.0, np.abs(ref).max())
