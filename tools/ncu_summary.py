@@ -1,5 +1,5 @@
-"""tools/ncu_summary.py <report.ncu-rep> [...] -- the handful of numbers the roofline claims rest on, as text (the
-.ncu-rep files are git-ignored; these summaries are what gets committed under profiles/)."""
+"""tools/ncu_summary.py <report.ncu-rep> [...] -- the handful of numbers the roofline claims rest on, as text (a
+readable companion of the .ncu-rep files committed under profiles/)."""
 import csv, subprocess, sys
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
